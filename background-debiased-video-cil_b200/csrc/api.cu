@@ -1,0 +1,454 @@
+// extern "C" entry points of libbgdebias_b200.so (see include/bgdebias.h) and the host-side
+// plumbing they share: error state, device properties, the per-thread workspace, and the pinned
+// staging pipeline behind the host-buffer calls.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "bgd_common.cuh"
+
+namespace bgd {
+
+// ---- error state / accounting ----------------------------------------------------------------
+std::string &last_error_ref()
+{
+    static thread_local std::string s;
+    return s;
+}
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_variant{BGD_MEDIAN_AUTO};
+
+// ---- device properties ------------------------------------------------------------------------
+int get_device_props(int device, DeviceProps *out)
+{
+    static std::mutex mu;
+    static DeviceProps cache[64];
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(BGD_ERR_NO_DEVICE, "no CUDA device available (%s)", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(BGD_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 64 && cache[device].ok) { *out = cache[device]; return BGD_OK; }
+    cudaDeviceProp p;
+    BGD_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    DeviceProps d;
+    d.sm_count = p.multiProcessorCount;
+    d.cc_major = p.major;
+    d.cc_minor = p.minor;
+    d.smem_optin = (int64_t)p.sharedMemPerBlockOptin;
+    d.total_mem = (int64_t)p.totalGlobalMem;
+    d.ok = true;
+    if (device < 64) cache[device] = d;
+    *out = d;
+    return BGD_OK;
+}
+
+int current_device_props(DeviceProps *out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BGD_ERR_NO_DEVICE, "no CUDA device available (%s)", cudaGetErrorString(e));
+    }
+    if (int rc = get_device_props(dev, out)) return rc;
+    if (out->cc_major != 10)
+        return fail(BGD_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                    out->cc_major, out->cc_minor);
+    return BGD_OK;
+}
+
+// ---- workspace --------------------------------------------------------------------------------
+int Workspace::acquire(size_t need)
+{
+    int dev = 0;
+    BGD_CUDA_TRY(cudaGetDevice(&dev));
+    if (ready) BGD_CUDA_TRY(cudaEventSynchronize(ready));   // previous upload consumed
+    if (dev != device || need > bytes) {
+        if (d_ptr) cudaFree(d_ptr);
+        if (h_pinned) cudaFreeHost(h_pinned);
+        d_ptr = h_pinned = nullptr;
+        bytes = 0;
+        size_t cap = std::max<size_t>(need, 1 << 16);
+        cap = (cap + 4095) & ~(size_t)4095;
+        BGD_CUDA_TRY(cudaMalloc(&d_ptr, cap));
+        BGD_CUDA_TRY(cudaMallocHost(&h_pinned, cap));
+        bytes = cap;
+        device = dev;
+        if (!ready) BGD_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    }
+    return BGD_OK;
+}
+
+int Workspace::release(cudaStream_t stream)
+{
+    if (ready) BGD_CUDA_TRY(cudaEventRecord(ready, stream));
+    return BGD_OK;
+}
+
+Workspace &thread_workspace()
+{
+    static thread_local Workspace ws;
+    return ws;
+}
+
+// ---- median dispatch -------------------------------------------------------------------------
+static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
+                                  uint8_t *d_out, cudaStream_t stream)
+{
+    if (V < 0 || N < 0) return fail(BGD_ERR_INVALID, "median: negative size");
+    if (V == 0) return BGD_OK;
+    if (!h_offsets) return fail(BGD_ERR_INVALID, "median: null offsets");
+    int64_t T_max = 0;
+    for (int64_t v = 0; v < V; ++v) {
+        const int64_t T = h_offsets[v + 1] - h_offsets[v];
+        // reference: np.median([]) is nan and the JPEG write raises (extract_background.py:73-74)
+        if (T <= 0) return fail(BGD_ERR_INVALID, "median: video %lld has no frames", (long long)v);
+        T_max = std::max(T_max, T);
+    }
+    if (N == 0) return BGD_OK;
+    if (!d_frames || !d_out) return fail(BGD_ERR_INVALID, "median: null pointer");
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+
+    const int variant = g_variant.load();
+    const bool aligned = reinterpret_cast<uintptr_t>(d_frames) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
+    bool bitsliced = aligned && median_bitsliced_supports(T_max, N);
+    if (variant == BGD_MEDIAN_BITSLICED && !bitsliced)
+        return fail(BGD_ERR_UNSUPPORTED,
+                    "median: bit-sliced variant needs N %% 16 == 0, 16-byte aligned buffers and T <= 576 (T=%lld N=%lld)",
+                    (long long)T_max, (long long)N);
+    if (variant == BGD_MEDIAN_SWAR) bitsliced = false;
+    if (bitsliced) return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
+
+    // generic variant: tables row0[V] | T[V]; grid.y carries the video index, 65535 per launch
+    Workspace &ws = thread_workspace();
+    if (int rc = ws.acquire((size_t)V * 12)) return rc;
+    int64_t *h_row0 = static_cast<int64_t *>(ws.h_pinned);
+    int32_t *h_T = reinterpret_cast<int32_t *>(h_row0 + V);
+    for (int64_t v = 0; v < V; ++v) {
+        h_row0[v] = h_offsets[v];
+        h_T[v] = (int32_t)(h_offsets[v + 1] - h_offsets[v]);
+    }
+    BGD_CUDA_TRY(cudaMemcpyAsync(ws.d_ptr, ws.h_pinned, (size_t)V * 12, cudaMemcpyHostToDevice, stream));
+    const int64_t *d_row0 = static_cast<const int64_t *>(ws.d_ptr);
+    const int32_t *d_T = reinterpret_cast<const int32_t *>(d_row0 + V);
+    int rc = BGD_OK;
+    for (int64_t v0 = 0; v0 < V && rc == BGD_OK; v0 += 65535) {
+        const int64_t nv = std::min<int64_t>(65535, V - v0);
+        rc = launch_median_swar(d_frames, d_row0 + v0, d_T + v0, nv, N, d_out + v0 * N, (int)std::min<int64_t>(T_max, 1 << 30), stream);
+    }
+    const int rc2 = ws.release(stream);
+    return rc ? rc : rc2;
+}
+
+// ---- pinned staging for the host-buffer calls --------------------------------------------------
+// Two pinned slabs + two device slabs per host thread; a chunk of whole videos is packed into a
+// pinned slab by the CPU while the previous chunk's copy and kernel run on the other slab.
+struct Stager {
+    static constexpr int kSlots = 2;
+    uint8_t *h_in[kSlots] = {nullptr, nullptr};
+    uint8_t *d_in[kSlots] = {nullptr, nullptr};
+    uint8_t *h_out[kSlots] = {nullptr, nullptr};
+    uint8_t *d_out[kSlots] = {nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;
+    cudaStream_t stream[kSlots] = {nullptr, nullptr};
+    cudaEvent_t done[kSlots] = {nullptr, nullptr};
+    int device = -1;
+
+    int ensure(int dev, size_t in_bytes, size_t out_bytes)
+    {
+        BGD_CUDA_TRY(cudaSetDevice(dev));
+        if (dev != device) {
+            release_all();
+            device = dev;
+            for (int s = 0; s < kSlots; ++s) {
+                BGD_CUDA_TRY(cudaStreamCreateWithFlags(&stream[s], cudaStreamNonBlocking));
+                BGD_CUDA_TRY(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+            }
+        }
+        if (in_bytes > in_cap) {
+            for (int s = 0; s < kSlots; ++s) {
+                if (h_in[s]) cudaFreeHost(h_in[s]);
+                if (d_in[s]) cudaFree(d_in[s]);
+                h_in[s] = d_in[s] = nullptr;
+            }
+            in_cap = 0;
+            for (int s = 0; s < kSlots; ++s) {
+                BGD_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_in[s]), in_bytes));
+                BGD_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_in[s]), in_bytes));
+            }
+            in_cap = in_bytes;
+        }
+        if (out_bytes > out_cap) {
+            for (int s = 0; s < kSlots; ++s) {
+                if (h_out[s]) cudaFreeHost(h_out[s]);
+                if (d_out[s]) cudaFree(d_out[s]);
+                h_out[s] = d_out[s] = nullptr;
+            }
+            out_cap = 0;
+            for (int s = 0; s < kSlots; ++s) {
+                BGD_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_out[s]), out_bytes));
+                BGD_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_out[s]), out_bytes));
+            }
+            out_cap = out_bytes;
+        }
+        return BGD_OK;
+    }
+    void release_all()
+    {
+        for (int s = 0; s < kSlots; ++s) {
+            if (h_in[s]) cudaFreeHost(h_in[s]);
+            if (d_in[s]) cudaFree(d_in[s]);
+            if (h_out[s]) cudaFreeHost(h_out[s]);
+            if (d_out[s]) cudaFree(d_out[s]);
+            if (stream[s]) cudaStreamDestroy(stream[s]);
+            if (done[s]) cudaEventDestroy(done[s]);
+            h_in[s] = d_in[s] = h_out[s] = d_out[s] = nullptr;
+            stream[s] = nullptr;
+            done[s] = nullptr;
+        }
+        in_cap = out_cap = 0;
+    }
+};
+
+static Stager &thread_stager()
+{
+    static thread_local Stager st;
+    return st;
+}
+
+static size_t staging_slab_bytes()
+{
+    size_t mb = 256;
+    if (const char *s = getenv("BGD_STAGING_SLAB_MB")) mb = (size_t)std::max(1, atoi(s));
+    return mb << 20;
+}
+
+// frames given as per-frame pointers (frame_ptrs[row]) or as one block (frames + row * N)
+static int median_host_pipeline(const uint8_t *const *frame_ptrs, const uint8_t *frames, const int64_t *h_offsets,
+                                int64_t V, int64_t N, uint8_t *h_out, int device)
+{
+    if (V < 0 || N < 0) return fail(BGD_ERR_INVALID, "median: negative size");
+    if (V == 0) return BGD_OK;
+    if (!h_offsets || (!frame_ptrs && !frames) || !h_out) return fail(BGD_ERR_INVALID, "median: null pointer");
+    int64_t T_max = 0;
+    for (int64_t v = 0; v < V; ++v) {
+        const int64_t T = h_offsets[v + 1] - h_offsets[v];
+        if (T <= 0) return fail(BGD_ERR_INVALID, "median: video %lld has no frames", (long long)v);
+        T_max = std::max(T_max, T);
+    }
+    if (N == 0) return BGD_OK;
+    DeviceProps dp;
+    if (int rc = get_device_props(device, &dp)) return rc;
+    BGD_CUDA_TRY(cudaSetDevice(device));
+
+    const size_t slab = std::max<size_t>(staging_slab_bytes(), (size_t)T_max * N);
+    // chunks of whole videos that fit a slab
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    for (int64_t v = 0; v < V;) {
+        int64_t e = v;
+        size_t bytes = 0;
+        while (e < V && bytes + (size_t)(h_offsets[e + 1] - h_offsets[e]) * N <= slab) {
+            bytes += (size_t)(h_offsets[e + 1] - h_offsets[e]) * N;
+            ++e;
+        }
+        chunks.emplace_back(v, e);
+        v = e;
+    }
+    int64_t max_videos = 0;
+    for (auto &c : chunks) max_videos = std::max(max_videos, c.second - c.first);
+    Stager &st = thread_stager();
+    if (int rc = st.ensure(device, slab, (size_t)max_videos * N)) return rc;
+
+    std::vector<int64_t> local;
+    int pending_slot_chunk[Stager::kSlots] = {-1, -1};
+    auto drain = [&](int slot) -> int {
+        if (pending_slot_chunk[slot] < 0) return BGD_OK;
+        BGD_CUDA_TRY(cudaEventSynchronize(st.done[slot]));
+        const auto &c = chunks[pending_slot_chunk[slot]];
+        std::memcpy(h_out + c.first * N, st.h_out[slot], (size_t)(c.second - c.first) * N);
+        pending_slot_chunk[slot] = -1;
+        return BGD_OK;
+    };
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const int slot = (int)(ci % Stager::kSlots);
+        if (int rc = drain(slot)) return rc;
+        const int64_t v0 = chunks[ci].first, v1 = chunks[ci].second;
+        const int64_t r0 = h_offsets[v0], r1 = h_offsets[v1];
+        // pack the chunk into the pinned slab (gathers separately allocated frames)
+        if (frame_ptrs) {
+            for (int64_t r = r0; r < r1; ++r) std::memcpy(st.h_in[slot] + (size_t)(r - r0) * N, frame_ptrs[r], (size_t)N);
+        } else {
+            std::memcpy(st.h_in[slot], frames + (size_t)r0 * N, (size_t)(r1 - r0) * N);
+        }
+        cudaStream_t s = st.stream[slot];
+        BGD_CUDA_TRY(cudaMemcpyAsync(st.d_in[slot], st.h_in[slot], (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, s));
+        local.resize((size_t)(v1 - v0 + 1));
+        for (int64_t v = v0; v <= v1; ++v) local[(size_t)(v - v0)] = h_offsets[v] - r0;
+        if (int rc = median_varlen_dispatch(st.d_in[slot], local.data(), v1 - v0, N, st.d_out[slot], s)) return rc;
+        BGD_CUDA_TRY(cudaMemcpyAsync(st.h_out[slot], st.d_out[slot], (size_t)(v1 - v0) * N, cudaMemcpyDeviceToHost, s));
+        BGD_CUDA_TRY(cudaEventRecord(st.done[slot], s));
+        pending_slot_chunk[slot] = (int)ci;
+    }
+    for (int slot = 0; slot < Stager::kSlots; ++slot)
+        if (int rc = drain(slot)) return rc;
+    return BGD_OK;
+}
+
+}  // namespace bgd
+
+// =================================================================================================
+using namespace bgd;
+
+extern "C" {
+
+int bgd_abi_version(void) { return BGD_ABI_VERSION; }
+
+const char *bgd_last_error(void) { return last_error_ref().c_str(); }
+
+int bgd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_optin_bytes,
+                    int64_t *total_mem_bytes)
+{
+    DeviceProps d;
+    if (int rc = get_device_props(device, &d)) return rc;
+    if (sm_count) *sm_count = d.sm_count;
+    if (cc_major) *cc_major = d.cc_major;
+    if (cc_minor) *cc_minor = d.cc_minor;
+    if (smem_optin_bytes) *smem_optin_bytes = d.smem_optin;
+    if (total_mem_bytes) *total_mem_bytes = d.total_mem;
+    return BGD_OK;
+}
+
+int64_t bgd_kernel_launch_count(void) { return g_launches.load(); }
+
+int bgd_median_set_variant(int variant)
+{
+    if (variant != BGD_MEDIAN_AUTO && variant != BGD_MEDIAN_SWAR && variant != BGD_MEDIAN_BITSLICED)
+        return fail(BGD_ERR_INVALID, "unknown median variant %d", variant);
+    g_variant.store(variant);
+    return BGD_OK;
+}
+
+int bgd_median_get_variant(void) { return g_variant.load(); }
+
+int bgd_temporal_median_u8(const uint8_t *d_frames, int64_t T, int64_t N, uint8_t *d_out, void *stream)
+{
+    const int64_t offs[2] = {0, T};
+    return median_varlen_dispatch(d_frames, offs, 1, N, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_temporal_median_varlen_u8(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
+                                  uint8_t *d_out, void *stream)
+{
+    if (V > 0 && h_offsets) {
+        for (int64_t v = 0; v < V; ++v)
+            if (h_offsets[v + 1] < h_offsets[v]) return fail(BGD_ERR_INVALID, "median: offsets must be non-decreasing");
+    }
+    return median_varlen_dispatch(d_frames, h_offsets, V, N, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_temporal_median_u8_host(const uint8_t *const *h_frame_ptrs, int64_t T, int64_t N, uint8_t *h_out, int device)
+{
+    if (!h_frame_ptrs) return fail(BGD_ERR_INVALID, "median: null frame pointer list");
+    const int64_t offs[2] = {0, T};
+    return median_host_pipeline(h_frame_ptrs, nullptr, offs, 1, N, h_out, device);
+}
+
+int bgd_temporal_median_varlen_u8_host(const uint8_t *h_frames, const int64_t *h_offsets, int64_t V, int64_t N,
+                                       uint8_t *h_out, int device)
+{
+    if (V > 0 && h_offsets) {
+        for (int64_t v = 0; v < V; ++v)
+            if (h_offsets[v + 1] < h_offsets[v]) return fail(BGD_ERR_INVALID, "median: offsets must be non-decreasing");
+        if (h_offsets[0] != 0 && !h_frames) return fail(BGD_ERR_INVALID, "median: null pointer");
+    }
+    return median_host_pipeline(nullptr, h_frames, h_offsets, V, N, h_out, device);
+}
+
+int bgd_bgmix_blend_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W, const float *d_bg_pool,
+                        int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx, const int32_t *d_top,
+                        const int32_t *d_left, const uint8_t *d_apply, const float *d_fg_lut, const float *h_bg_mean,
+                        const float *h_bg_std, double alpha, int layout, float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    return launch_bgmix(d_fg, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
+                        h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_bgmix_blend_u8pool_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W,
+                               const uint8_t *d_bg_pool, int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx,
+                               const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
+                               const float *d_fg_lut, const float *h_bg_mean, const float *h_bg_std, double alpha,
+                               int layout, float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    return launch_bgmix(d_fg, B, T, H, W, d_bg_pool, true, P, Hb, Wb, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
+                        h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t H, int64_t W, const float *d_bg_pool,
+                             int64_t P, int64_t Hb, int64_t Wb, const int32_t *h_bg_idx, const int32_t *h_top,
+                             const int32_t *h_left, const uint8_t *h_apply, const float *d_fg_lut,
+                             const float *h_bg_mean, const float *h_bg_std, double alpha, int layout, float *d_out,
+                             double *h_checksum, int device)
+{
+    if (B < 0 || T < 0 || H < 0 || W < 0) return fail(BGD_ERR_INVALID, "bgmix: negative size");
+    if (B == 0 || T == 0 || H == 0 || W == 0) { if (h_checksum) *h_checksum = 0.0; return BGD_OK; }
+    if (!h_fg || !h_bg_idx || !h_top || !h_left || !h_apply) return fail(BGD_ERR_INVALID, "bgmix: null host pointer");
+    // the reference's RandomCrop raises when the crop does not fit; validate here, on host values
+    for (int64_t b = 0; b < B; ++b) {
+        if (!h_apply[b]) continue;
+        if (h_bg_idx[b] < 0 || h_bg_idx[b] >= P) return fail(BGD_ERR_INVALID, "bgmix: bg_idx[%lld]=%d outside pool of %lld", (long long)b, h_bg_idx[b], (long long)P);
+        if (h_top[b] < 0 || h_top[b] + H > Hb || h_left[b] < 0 || h_left[b] + W > Wb)
+            return fail(BGD_ERR_INVALID, "bgmix: crop of sample %lld leaves the pool image", (long long)b);
+    }
+    DeviceProps dp;
+    if (int rc = get_device_props(device, &dp)) return rc;
+    BGD_CUDA_TRY(cudaSetDevice(device));
+    const size_t fg_bytes = (size_t)B * T * H * W * 3;
+    const size_t par_bytes = (size_t)B * 13 + 64;
+    Stager &st = thread_stager();
+    if (int rc = st.ensure(device, fg_bytes + par_bytes + 64, 64)) return rc;
+    cudaStream_t s = st.stream[0];
+    uint8_t *hp = st.h_in[0], *dp_ = st.d_in[0];
+    std::memcpy(hp, h_fg, fg_bytes);
+    size_t o = (fg_bytes + 15) & ~(size_t)15;
+    std::memcpy(hp + o, h_bg_idx, (size_t)B * 4);
+    std::memcpy(hp + o + (size_t)B * 4, h_top, (size_t)B * 4);
+    std::memcpy(hp + o + (size_t)B * 8, h_left, (size_t)B * 4);
+    std::memcpy(hp + o + (size_t)B * 12, h_apply, (size_t)B);
+    BGD_CUDA_TRY(cudaMemcpyAsync(dp_, hp, o + (size_t)B * 13, cudaMemcpyHostToDevice, s));
+    const int32_t *d_idx = reinterpret_cast<const int32_t *>(dp_ + o);
+    if (int rc = launch_bgmix(dp_, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_idx, d_idx + B, d_idx + 2 * B,
+                              dp_ + o + (size_t)B * 12, d_fg_lut, h_bg_mean, h_bg_std, alpha, layout, d_out, s))
+        return rc;
+    if (h_checksum) {
+        double *d_sum = reinterpret_cast<double *>(st.d_out[0]);
+        if (int rc = launch_sum_f32(d_out, (int64_t)B * T * 3 * H * W, d_sum, s)) return rc;
+        BGD_CUDA_TRY(cudaMemcpyAsync(st.h_out[0], d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    BGD_CUDA_TRY(cudaStreamSynchronize(s));
+    if (h_checksum) std::memcpy(h_checksum, st.h_out[0], sizeof(double));
+    return BGD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Shared helpers for libbgdebias_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "bgdebias.h"
+
+namespace bgd {
+
+// ---- error state (per host thread) -------------------------------------------------------
+std::string &last_error_ref();
+int fail(int code, const char *fmt, ...);
+
+#define BGD_CUDA_TRY(expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::bgd::fail(BGD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+// ---- launch accounting -------------------------------------------------------------------
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- device properties, cached per device ------------------------------------------------
+struct DeviceProps {
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    int64_t smem_optin = 0;
+    int64_t total_mem = 0;
+    bool ok = false;
+};
+int get_device_props(int device, DeviceProps *out);   // returns bgd_status
+int current_device_props(DeviceProps *out);
+
+// ---- kernels' host launchers (defined in the .cu files) ----------------------------------
+int launch_median_swar(const uint8_t *d_frames, const int64_t *d_row0, const int32_t *d_T,
+                       int64_t V, int64_t N, uint8_t *d_out, int T_max, cudaStream_t stream);
+
+struct MedianWork;  // planner output, see median_bitsliced.cu
+int median_bitsliced_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
+                            uint8_t *d_out, cudaStream_t stream);
+bool median_bitsliced_supports(int64_t T_max, int64_t N);
+
+int launch_bgmix(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W, const void *d_pool,
+                 bool pool_is_u8, int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx,
+                 const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
+                 const float *d_lut, const float *h_mean, const float *h_std, double alpha,
+                 int layout, float *d_out, cudaStream_t stream);
+int launch_sum_f32(const float *d_x, int64_t n, double *d_sum, cudaStream_t stream);
+
+// ---- small device workspace that survives across calls (per device, per host thread) -----
+// Used for the per-launch tables (row offsets, frame counts, tile lists).  Stream-ordered use:
+// the caller uploads with cudaMemcpyAsync from the pinned mirror and launches on the same
+// stream; `acquire` waits for the previous user's event before the pinned mirror is rewritten.
+struct Workspace {
+    void *d_ptr = nullptr;
+    void *h_pinned = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t ready = nullptr;
+    int device = -1;
+    int acquire(size_t need);                 // ensures capacity and that the mirror is reusable
+    int release(cudaStream_t stream);         // records `ready` on the stream that used it
+};
+Workspace &thread_workspace();
+
+}  // namespace bgd

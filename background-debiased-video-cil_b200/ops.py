@@ -1,0 +1,148 @@
+"""``torch.ops.bgdebias.*`` -- the CUDA kernels of libbgdebias_b200.so as torch.library custom ops.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every op hands raw
+pointers, sizes and the current ``cudaStream_t`` to the C ABI (include/bgdebias.h).  The ops are
+registered for CUDA tensors only -- CPU tensors raise ``NotImplementedError`` -- and need the
+built library (``ImportError`` otherwise).  Ops are stream-ordered and never synchronise.
+
+    bgdebias::temporal_median(Tensor frames) -> Tensor
+        frames uint8 [T, ...] -> uint8 [...]; np.median(frames, 0).astype(uint8), bit-exact
+        (cil_tools/extract_background.py:73).
+    bgdebias::temporal_median_varlen(Tensor frames, Tensor offsets) -> Tensor
+        frames uint8 [sum T, ...], offsets int64/int32 CPU tensor [V+1] -> uint8 [V, ...]
+        (what extract_background.py:102-109 does video by video).
+    bgdebias::bgmix_blend(Tensor fg, Tensor bg_pool, Tensor bg_idx, Tensor top, Tensor left,
+                          Tensor apply, Tensor fg_lut, Tensor bg_mean, Tensor bg_std,
+                          float alpha, str layout) -> Tensor
+        the batched form of BackgroundMixDataset._mix_background (libs/loader/comix_loader.py:138-145).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Sequence
+
+import torch
+
+from . import _cabi
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise ValueError(msg)
+
+
+# --------------------------------------------------------------------------- #
+# temporal median
+# --------------------------------------------------------------------------- #
+@torch.library.custom_op("bgdebias::temporal_median", mutates_args=(), device_types="cuda")
+def temporal_median(frames: torch.Tensor) -> torch.Tensor:
+    _require(frames.dtype == torch.uint8, "temporal_median: frames must be uint8")
+    _require(frames.dim() >= 1, "temporal_median: frames must be [T, ...]")
+    T = frames.shape[0]
+    _require(T > 0, "temporal_median: zero frames (the reference fails here too: median of nothing)")
+    frames = frames.contiguous()
+    out = torch.empty(frames.shape[1:], dtype=torch.uint8, device=frames.device)
+    N = out.numel()
+    with torch.cuda.device(frames.device):
+        _cabi.check(_cabi.lib().bgd_temporal_median_u8(frames.data_ptr(), T, N, out.data_ptr(),
+                                                       _stream_ptr(frames.device)))
+    return out
+
+
+@temporal_median.register_fake
+def _(frames):
+    return frames.new_empty(frames.shape[1:])
+
+
+@torch.library.custom_op("bgdebias::temporal_median_varlen", mutates_args=(), device_types="cuda")
+def temporal_median_varlen(frames: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    _require(frames.dtype == torch.uint8, "temporal_median_varlen: frames must be uint8")
+    _require(frames.dim() >= 1, "temporal_median_varlen: frames must be [sum T, ...]")
+    _require(offsets.dim() == 1 and offsets.numel() >= 1, "temporal_median_varlen: offsets must be [V+1]")
+    _require(offsets.dtype in (torch.int64, torch.int32), "temporal_median_varlen: offsets must be int32/int64")
+    offs = offsets.detach().to("cpu", torch.int64).contiguous()          # the planner runs on the host
+    V = offs.numel() - 1
+    _require(int(offs[0]) >= 0 and int(offs[-1]) <= frames.shape[0], "temporal_median_varlen: offsets out of range")
+    frames = frames.contiguous()
+    out = torch.empty((V,) + tuple(frames.shape[1:]), dtype=torch.uint8, device=frames.device)
+    N = math.prod(frames.shape[1:])
+    optr = ctypes.cast(offs.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+    with torch.cuda.device(frames.device):
+        _cabi.check(_cabi.lib().bgd_temporal_median_varlen_u8(frames.data_ptr(), optr, V, N, out.data_ptr(),
+                                                              _stream_ptr(frames.device)))
+    return out
+
+
+@temporal_median_varlen.register_fake
+def _(frames, offsets):
+    return frames.new_empty((offsets.shape[0] - 1,) + tuple(frames.shape[1:]))
+
+
+# --------------------------------------------------------------------------- #
+# BG-mix blend
+# --------------------------------------------------------------------------- #
+def _host3(t: torch.Tensor, name: str):
+    _require(t.numel() == 3, f"bgmix_blend: {name} must have 3 values")
+    return _cabi.f32x3(t.detach().to("cpu", torch.float32).tolist())
+
+
+@torch.library.custom_op("bgdebias::bgmix_blend", mutates_args=(), device_types="cuda")
+def bgmix_blend(fg: torch.Tensor, bg_pool: torch.Tensor, bg_idx: torch.Tensor, top: torch.Tensor,
+                left: torch.Tensor, apply: torch.Tensor, fg_lut: torch.Tensor, bg_mean: torch.Tensor,
+                bg_std: torch.Tensor, alpha: float, layout: str) -> torch.Tensor:
+    _require(fg.dtype == torch.uint8 and fg.dim() == 5 and fg.shape[-1] == 3,
+             "bgmix_blend: fg must be uint8 [B, T, H, W, 3]")
+    _require(bg_pool.dim() == 4 and bg_pool.shape[1] == 3 and bg_pool.dtype in (torch.float32, torch.uint8),
+             "bgmix_blend: bg_pool must be float32 or uint8 [P, 3, Hb, Wb]")
+    _require(layout in _cabi.LAYOUTS, f"bgmix_blend: layout must be one of {sorted(_cabi.LAYOUTS)}")
+    B, T, H, W, _ = fg.shape
+    P, _, Hb, Wb = bg_pool.shape
+    dev = fg.device
+    for name, t, dt in (("bg_idx", bg_idx, torch.int32), ("top", top, torch.int32), ("left", left, torch.int32),
+                        ("apply", apply, torch.uint8)):
+        _require(t.dtype == dt and t.dim() == 1 and t.shape[0] == B, f"bgmix_blend: {name} must be {dt} [B]")
+        _require(t.device == dev, f"bgmix_blend: {name} must be on {dev}")
+    _require(fg_lut.dtype == torch.float32 and tuple(fg_lut.shape) == (3, 256) and fg_lut.device == dev,
+             "bgmix_blend: fg_lut must be float32 [3, 256] on the device")
+    _require(bg_pool.device == dev, "bgmix_blend: bg_pool must be on the same device as fg")
+    fg, bg_pool = fg.contiguous(), bg_pool.contiguous()
+    bg_idx, top, left, apply, fg_lut = (x.contiguous() for x in (bg_idx, top, left, apply, fg_lut))
+    shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    fn = _cabi.lib().bgd_bgmix_blend_f32 if bg_pool.dtype == torch.float32 else _cabi.lib().bgd_bgmix_blend_u8pool_f32
+    with torch.cuda.device(dev):
+        _cabi.check(fn(fg.data_ptr(), B, T, H, W, bg_pool.data_ptr(), P, Hb, Wb, bg_idx.data_ptr(), top.data_ptr(),
+                       left.data_ptr(), apply.data_ptr(), fg_lut.data_ptr(), _host3(bg_mean, "bg_mean"),
+                       _host3(bg_std, "bg_std"), float(alpha), _cabi.LAYOUTS[layout], out.data_ptr(),
+                       _stream_ptr(dev)))
+    return out
+
+
+@bgmix_blend.register_fake
+def _(fg, bg_pool, bg_idx, top, left, apply, fg_lut, bg_mean, bg_std, alpha, layout):
+    B, T, H, W, _ = fg.shape
+    shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
+    return fg.new_empty(shape, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------- #
+# host-side table for the foreground normalisation
+# --------------------------------------------------------------------------- #
+def make_fg_lut(mean: Sequence[float], std: Sequence[float], device=None) -> torch.Tensor:
+    """[3, 256] fp32 table of mmaction ``Normalize`` (mmcv.imnormalize_) outputs per uint8 level.
+
+    mmcv evaluates ``cv2.subtract(img_f32, float64(mean)); cv2.multiply(img_f32, 1/float64(std))``,
+    i.e. ``f32(f64(f32(x) - f32(mean)) * (1 / f64(std)))``: an fp32 subtract, then a multiply whose
+    scale is a double.  Built once per (mean, std) on the host in exactly that precision.
+    """
+    mean64 = torch.tensor([float(m) for m in mean], dtype=torch.float64)
+    std64 = torch.tensor([float(s) for s in std], dtype=torch.float64)
+    x = torch.arange(256, dtype=torch.float32)
+    d32 = x[None, :] - mean64.to(torch.float32)[:, None]
+    lut = (d32.to(torch.float64) * (1.0 / std64)[:, None]).to(torch.float32)
+    return lut.to(device) if device is not None else lut

@@ -1,0 +1,152 @@
+/*
+ * bgdebias.h -- C ABI of libbgdebias_b200.so
+ *
+ * B200 (sm_100a) replacement for the background-debiasing data path of
+ * NinV/Background-Debiased-Video-CIL.  Plain pointers and sizes only: no torch types, no C++
+ * types.  Every entry point names the reference code it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - every function returns a bgd_status (0 = BGD_OK); on failure bgd_last_error() holds a
+ *     message for the calling thread.  The reference signals errors with Python exceptions;
+ *     the Python host layer turns a non-zero status into RuntimeError/ValueError.
+ *   - "d_" pointers are device memory on the current CUDA device, "h_" pointers are host memory.
+ *   - device entry points are stream-ordered: they enqueue work on `stream` (a cudaStream_t,
+ *     NULL = default stream) and return without synchronising.  Host entry points copy in,
+ *     compute, copy out and return when the result is in the host buffer.
+ *   - there is no CPU fallback: without a usable sm_100 device every compute call fails with
+ *     BGD_ERR_NO_DEVICE / BGD_ERR_CUDA.
+ */
+#ifndef BGDEBIAS_H_
+#define BGDEBIAS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGD_ABI_VERSION 1
+
+typedef enum bgd_status {
+    BGD_OK = 0,
+    BGD_ERR_INVALID = 1,      /* bad argument (null pointer, T == 0, negative size, ...) */
+    BGD_ERR_CUDA = 2,         /* a CUDA runtime call failed; see bgd_last_error() */
+    BGD_ERR_UNSUPPORTED = 3,  /* valid request this build cannot serve */
+    BGD_ERR_NO_DEVICE = 4     /* no CUDA device / not an sm_100 device */
+} bgd_status;
+
+/* Output layouts of the blend.  NTCHW is what the reference's DataLoader hands the model:
+ * per-sample FormatShape('NCHW') gives [T,3,H,W] and default_collate stacks to [B,T,3,H,W]
+ * (libs/cil/cil.py:203-210).  NCTHW is the permuted variant BASELINE.json mentions. */
+#define BGD_LAYOUT_NTCHW 0
+#define BGD_LAYOUT_NCTHW 1
+
+/* Median kernel variants (for differential testing; AUTO is the product path). */
+#define BGD_MEDIAN_AUTO      0
+#define BGD_MEDIAN_SWAR      1   /* thread-per-4-columns byte-SIMD binary search; any T, any N */
+#define BGD_MEDIAN_BITSLICED 2   /* TMA-staged bit-sliced radix select; needs N % 16 == 0      */
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+int bgd_abi_version(void);
+const char *bgd_last_error(void);
+
+/* Properties of CUDA device `device`; any out pointer may be NULL. */
+int bgd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                    int64_t *smem_optin_bytes, int64_t *total_mem_bytes);
+
+/* Number of kernels this library has launched since load (all threads). */
+int64_t bgd_kernel_launch_count(void);
+
+/* Select the median kernel variant used by the entry points below (process-wide). */
+int bgd_median_set_variant(int variant);
+int bgd_median_get_variant(void);
+
+/* ---- temporal median ---------------------------------------------------------------------
+ * Replaces   median_frame = np.median(frames, axis=0).astype(dtype=np.uint8)
+ *   cil_tools/extract_background.py:73   (CLI variant of bg_extraction_tmf, :42-75)
+ *   libs/loader/comix_loader.py:161      (rawframes variant, :148-164)
+ * Semantics (bit-exact): out[n] = (s[(T-1)/2] + s[T/2]) >> 1 with s = sort(frames[:, n]).
+ * A video is a [T][N] uint8 matrix, N = H*W*3 bytes per frame, rows contiguous.
+ */
+
+/* One video resident in device memory. d_frames [T][N], d_out [N]. */
+int bgd_temporal_median_u8(const uint8_t *d_frames, int64_t T, int64_t N, uint8_t *d_out,
+                           void *stream);
+
+/* V videos concatenated along T (same N): video v owns rows h_offsets[v] .. h_offsets[v+1]-1.
+ * This is one call for what bg_extract_multiple (extract_background.py:102-109) does video by
+ * video.  h_offsets is a HOST array of V+1 non-decreasing row indices; every video needs at
+ * least one frame.  d_out [V][N]. */
+int bgd_temporal_median_varlen_u8(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V,
+                                  int64_t N, uint8_t *d_out, void *stream);
+
+/* Host-buffer form of the same computation: the frames are T separately allocated host
+ * buffers of N bytes each (the `frames` list of extract_background.py:48-60; pass pointers
+ * into one block if they are contiguous).  Stages through pinned memory, runs the kernel,
+ * copies the [N] result back to h_out.  `device` = CUDA device ordinal. */
+int bgd_temporal_median_u8_host(const uint8_t *const *h_frame_ptrs, int64_t T, int64_t N,
+                                uint8_t *h_out, int device);
+
+/* Host-buffer form for a batch of videos in one contiguous host block h_frames [sum T][N]
+ * (pinned or pageable); results to h_out [V][N].  Copies and kernels are pipelined in chunks
+ * of whole videos through a pinned double buffer.  This is the call a worker of
+ * extract_background.py:154-162 would make for its slice of the video list. */
+int bgd_temporal_median_varlen_u8_host(const uint8_t *h_frames, const int64_t *h_offsets,
+                                       int64_t V, int64_t N, uint8_t *h_out, int device);
+
+/* ---- BG-mix blend ------------------------------------------------------------------------
+ * Replaces, for a whole batch in one launch,
+ *   libs/loader/comix_loader.py:138-145   BackgroundMixDataset._mix_background
+ *       bg    = Normalize(RandomCrop(Resize(bg)))                      (bg_pipeline, :72-75)
+ *       blend = imgs * (1 - alpha) + bg.view(1, 3, H, W) * alpha        (:142)
+ *   plus the mmaction Normalize + FormatShape('NCHW') that produced `imgs` from uint8 frames
+ *   (configs/ucf101/bgmix_plus_randAug/..._bgmix_plus_randAug.py:137-138), folded in as a
+ *   per-channel 256-entry table (d_fg_lut) so the foreground travels as uint8.
+ *
+ *   d_fg      [B][T][H][W][3] uint8 RGB        foreground clips after the geometric pipeline
+ *   d_bg_pool [P][3][Hb][Wb]  fp32             backgrounds AFTER Resize (values 0..255, not normalised)
+ *   d_bg_idx  [B] int32   pool slot per sample (ignored where apply == 0)
+ *   d_top, d_left [B] int32   RandomCrop offsets: rows top..top+H-1, cols left..left+W-1
+ *   d_apply   [B] uint8   1 = blend, 0 = foreground normalisation only (sample not mixed)
+ *   d_fg_lut  [3][256] fp32   normalised value of every uint8 level per channel
+ *   h_bg_mean, h_bg_std [3]  HOST fp32 arrays, torchvision Normalize parameters
+ *   alpha     blend weight of the background; (1 - alpha) is computed in double then rounded
+ *   d_out     fp32, BGD_LAYOUT_NTCHW: [B][T][3][H][W];  BGD_LAYOUT_NCTHW: [B][3][T][H][W]
+ * Arithmetic per element (each operation rounded to fp32, no FMA contraction):
+ *   fg = lut[c][x];  bg = (p - mean[c]) / std[c];  out = fg * f32(1-alpha) + bg * f32(alpha)
+ */
+int bgd_bgmix_blend_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W,
+                        const float *d_bg_pool, int64_t P, int64_t Hb, int64_t Wb,
+                        const int32_t *d_bg_idx, const int32_t *d_top, const int32_t *d_left,
+                        const uint8_t *d_apply, const float *d_fg_lut, const float *h_bg_mean,
+                        const float *h_bg_std, double alpha, int layout, float *d_out,
+                        void *stream);
+
+/* Same with a uint8 background pool [P][3][Hb][Wb] (values already at crop scale, e.g. a pool
+ * whose images need no Resize); 4x less pool memory and traffic. */
+int bgd_bgmix_blend_u8pool_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W,
+                               const uint8_t *d_bg_pool, int64_t P, int64_t Hb, int64_t Wb,
+                               const int32_t *d_bg_idx, const int32_t *d_top, const int32_t *d_left,
+                               const uint8_t *d_apply, const float *d_fg_lut,
+                               const float *h_bg_mean, const float *h_bg_std, double alpha,
+                               int layout, float *d_out, void *stream);
+
+/* Host-buffer form: foreground batch and per-sample parameters live in host memory (what a
+ * DataLoader collate hands over), the pool and the LUT are device resident.  Copies the inputs
+ * in, blends, leaves the training tensor in d_out (device) and returns after the stream is
+ * idle.  If h_checksum is not NULL it receives the sum of all output elements (double),
+ * computed on device and copied back. */
+int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t H, int64_t W,
+                             const float *d_bg_pool, int64_t P, int64_t Hb, int64_t Wb,
+                             const int32_t *h_bg_idx, const int32_t *h_top, const int32_t *h_left,
+                             const uint8_t *h_apply, const float *d_fg_lut, const float *h_bg_mean,
+                             const float *h_bg_std, double alpha, int layout, float *d_out,
+                             double *h_checksum, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGDEBIAS_H_ */
