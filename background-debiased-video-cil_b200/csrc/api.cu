@@ -132,7 +132,7 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
     bool bitsliced = aligned && median_bitsliced_supports(T_max, N);
     if (variant == BGD_MEDIAN_BITSLICED && !bitsliced)
         return fail(BGD_ERR_UNSUPPORTED,
-                    "median: bit-sliced variant needs N %% 16 == 0, 16-byte aligned buffers and T <= 576 (T=%lld N=%lld)",
+                    "median: bit-sliced variant needs N %% 16 == 0, 16-byte aligned buffers and at most ~500 frames per video (T=%lld N=%lld)",
                     (long long)T_max, (long long)N);
     if (variant == BGD_MEDIAN_SWAR) bitsliced = false;
     if (bitsliced) return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);

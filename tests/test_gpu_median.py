@@ -53,13 +53,15 @@ def test_golden_reference_outputs(bgd, name, variant):
 
 
 T_VALUES = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 96, 100, 127, 128, 129,
-            179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 576]
+            179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 527, 528, 576]
 
 
 @pytest.mark.parametrize("variant", ["swar", "bitsliced"])
 @pytest.mark.parametrize("T", T_VALUES)
 def test_random_all_T(bgd, T, variant):
     ops, cabi = bgd
+    if variant == "bitsliced" and T > 528:
+        pytest.skip("bit-sliced variant holds at most 528 rows per CTA; AUTO falls back to the generic variant")
     cabi.set_median_variant({"swar": 1, "bitsliced": 2}[variant])
     rng = np.random.default_rng(1000 + T)
     N = 16 * int(rng.integers(1, 90))                     # ragged tile tails

@@ -1,0 +1,37 @@
+"""In-process sweep of the median planner knobs (development aid)."""
+import os, sys, pathlib, itertools
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+import bgdebias_b200.ops  # noqa
+from bgdebias_b200 import _cabi
+
+def run(fr, offs, iters=4):
+    torch.ops.bgdebias.temporal_median_varlen(fr, offs); torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.ops.bgdebias.temporal_median_varlen(fr, offs); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+N = int(os.environ.get("N", 230400)); V = int(os.environ.get("V", 64))
+cases = sys.argv[1:] or ["180", "181", "mixed"]
+Rs = [int(x) for x in os.environ.get("RS", "6,8,10,12").split(",")]
+THs = [int(x) for x in os.environ.get("THS", "192,256,384").split(",")]
+Cs = [int(x) for x in os.environ.get("CS", "2,3").split(",")]
+rng = np.random.default_rng(1)
+for case in cases:
+    Ts = rng.integers(120, 241, V) if case == "mixed" else np.full(V, int(case))
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64))
+    rows = int(offs[-1])
+    fr = torch.randint(0, 256, (rows, N), dtype=torch.uint8, device="cuda")
+    by = (rows + V) * N
+    _cabi.set_median_variant(0)
+    for R, TH, C in itertools.product(Rs, THs, Cs):
+        os.environ["BGD_MEDIAN_TARGET_R"] = str(R); os.environ["BGD_MEDIAN_TARGET_THREADS"] = str(TH); os.environ["BGD_MEDIAN_CTAS_PER_SM"] = str(C)
+        try:
+            ms = run(fr, offs)
+            print(f"T={case:>5s} R={R:2d} thr={TH:3d} ctas={C}: {ms:7.3f} ms {by/ms/1e6:7.1f} GB/s {rows/ms/1e3:6.2f} Mframes/s", flush=True)
+        except Exception as e:
+            print(f"T={case} R={R} thr={TH} ctas={C}: ERROR {e}", flush=True)
+    del fr
