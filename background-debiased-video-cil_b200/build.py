@@ -18,7 +18,8 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 OBJ = CSRC / "_obj"
 LIB = PKG / "libbgdebias_b200.so"
-SOURCES = ["api.cu", "median_swar.cu", "median_bitsliced.cu", "bgmix.cu"]
+SOURCES = ["api.cu", "median_swar.cu", "median_bitsliced.cu", "median_colplane.cu", "median_colplane_c1.cu",
+           "median_colplane_c2.cu", "median_colplane_c4.cu", "bgmix.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -129,13 +129,16 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
 
     const int variant = g_variant.load();
     const bool aligned = reinterpret_cast<uintptr_t>(d_frames) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
-    bool bitsliced = aligned && median_bitsliced_supports(T_max, N);
-    if (variant == BGD_MEDIAN_BITSLICED && !bitsliced)
+    const bool can_col = aligned && median_colplane_supports(T_max, N);
+    const bool can_bit = aligned && median_bitsliced_supports(T_max, N);
+    if ((variant == BGD_MEDIAN_COLPLANE && !can_col) || (variant == BGD_MEDIAN_BITSLICED && !can_bit))
         return fail(BGD_ERR_UNSUPPORTED,
-                    "median: bit-sliced variant needs N %% 16 == 0, 16-byte aligned buffers and at most ~500 frames per video (T=%lld N=%lld)",
+                    "median: the TMA variants need N %% 16 == 0, 16-byte aligned buffers and at most ~500 frames per video (T=%lld N=%lld)",
                     (long long)T_max, (long long)N);
-    if (variant == BGD_MEDIAN_SWAR) bitsliced = false;
-    if (bitsliced) return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
+    if (variant == BGD_MEDIAN_COLPLANE || (variant == BGD_MEDIAN_AUTO && can_col))
+        return median_colplane_varlen(d_frames, h_offsets, V, N, d_out, stream);
+    if (variant == BGD_MEDIAN_BITSLICED || (variant == BGD_MEDIAN_AUTO && can_bit))
+        return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
 
     // generic variant: tables row0[V] | T[V]; grid.y carries the video index, 65535 per launch
     Workspace &ws = thread_workspace();
@@ -340,7 +343,7 @@ int64_t bgd_kernel_launch_count(void) { return g_launches.load(); }
 
 int bgd_median_set_variant(int variant)
 {
-    if (variant != BGD_MEDIAN_AUTO && variant != BGD_MEDIAN_SWAR && variant != BGD_MEDIAN_BITSLICED)
+    if (variant < BGD_MEDIAN_AUTO || variant > BGD_MEDIAN_COLPLANE)
         return fail(BGD_ERR_INVALID, "unknown median variant %d", variant);
     g_variant.store(variant);
     return BGD_OK;

@@ -1,0 +1,171 @@
+// Host side of the column-plane median (see median_colplane.cuh): bucket the videos of a call by
+// kernel configuration (C, NW, parity), build the TMA tensor maps, launch one kernel per bucket.
+#include <algorithm>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "median_colplane.cuh"
+
+namespace bgd {
+
+namespace {
+
+using colplane::CParams;
+using colplane::kNumMaps;
+using colplane::kStripBytes;
+
+struct Key {
+    int C, NW, even;
+    bool operator<(const Key &o) const { return std::tie(C, NW, even) < std::tie(o.C, o.NW, o.even); }
+};
+
+struct Tuning {
+    int t_c4 = 96;     // T <= t_c4: 4 columns per thread (8 rows per plane word)
+    int t_c2 = 240;    // T <= t_c2: 2 columns per thread (16 rows per plane word)
+    int threads_c1 = 256, threads_c2 = 128, threads_c4 = 128;
+};
+
+Tuning read_tuning()
+{
+    Tuning t;
+    if (const char *s = getenv("BGD_COL_T_C4")) t.t_c4 = atoi(s);
+    if (const char *s = getenv("BGD_COL_T_C2")) t.t_c2 = atoi(s);
+    if (const char *s = getenv("BGD_COL_THREADS_C2")) t.threads_c2 = atoi(s) >= 256 ? 256 : 128;
+    if (const char *s = getenv("BGD_COL_THREADS_C4")) { const int v = atoi(s); t.threads_c4 = v >= 256 ? 256 : (v >= 192 ? 192 : (v >= 128 ? 128 : 64)); }
+    return t;
+}
+
+bool classify(int T, const Tuning &tn, Key *k)
+{
+    int C = T <= tn.t_c4 ? 4 : (T <= tn.t_c2 ? 2 : 1);
+    for (; C >= 1; C /= 2) {
+        const int rpw = 32 / C;
+        const int NW = (T + rpw - 1) / rpw;
+        if (NW <= (C == 1 ? 17 : 15)) {
+            *k = Key{C, NW, (T & 1) == 0};
+            return true;
+        }
+    }
+    return false;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn *out)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        BGD_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p)
+            return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *out = fn;
+    return BGD_OK;
+}
+
+}  // namespace
+
+bool median_colplane_supports(int64_t T_max, int64_t N)
+{
+    if (N <= 0 || N % 16 != 0 || N >= ((int64_t)1 << 31)) return false;
+    if (T_max < 1 || T_max > 544) return false;
+    Key k;
+    return classify((int)T_max, read_tuning(), &k);
+}
+
+int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, uint8_t *d_out,
+                           cudaStream_t stream)
+{
+    if (V == 0 || N == 0) return BGD_OK;
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    const Tuning tn = read_tuning();
+    EncodeTiledFn encode = nullptr;
+    if (int rc = get_encode_fn(&encode)) return rc;
+
+    const int64_t row_lo = h_offsets[0], row_hi = h_offsets[V];
+    if (row_hi - row_lo >= ((int64_t)1 << 31)) return fail(BGD_ERR_UNSUPPORTED, "median: more than 2^31 rows per call");
+    CParams prm{};
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)(row_hi - row_lo)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)N};
+        const cuuint32_t estride[2] = {1, 1};
+        void *base = const_cast<uint8_t *>(d_frames) + row_lo * N;
+        for (int k = 0; k < kNumMaps; ++k) {
+            const cuuint32_t box[2] = {(cuuint32_t)kStripBytes, (cuuint32_t)1 << k};
+            const CUresult r = encode(&prm.maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a box of %d rows", (int)r, 1 << k);
+        }
+    }
+
+    std::map<Key, std::vector<int64_t>> classes;
+    for (int64_t v = 0; v < V; ++v) {
+        Key k;
+        if (!classify((int)(h_offsets[v + 1] - h_offsets[v]), tn, &k))
+            return fail(BGD_ERR_UNSUPPORTED, "median (column-plane): video %lld has too many frames", (long long)v);
+        classes[k].push_back(v);
+    }
+
+    // one table upload for all classes: row0[V] | out[V] | T[V], in class order
+    Workspace &ws = thread_workspace();
+    const size_t tbl_bytes = (size_t)V * (8 + 8 + 4);
+    if (int rc = ws.acquire(tbl_bytes)) return rc;
+    int64_t *h_row0 = static_cast<int64_t *>(ws.h_pinned);
+    int64_t *h_out = h_row0 + V;
+    int32_t *h_T = reinterpret_cast<int32_t *>(h_out + V);
+    const int64_t *d_row0 = static_cast<const int64_t *>(ws.d_ptr);
+    const int64_t *d_outi = d_row0 + V;
+    const int32_t *d_T = reinterpret_cast<const int32_t *>(d_outi + V);
+    {
+        int64_t pos = 0;
+        for (auto &kv : classes)
+            for (int64_t v : kv.second) {
+                h_row0[pos] = h_offsets[v] - row_lo;
+                h_out[pos] = v;
+                h_T[pos] = (int32_t)(h_offsets[v + 1] - h_offsets[v]);
+                ++pos;
+            }
+    }
+    BGD_CUDA_TRY(cudaMemcpyAsync(ws.d_ptr, ws.h_pinned, tbl_bytes, cudaMemcpyHostToDevice, stream));
+
+    int64_t pos = 0;
+    int rc = BGD_OK;
+    for (auto &kv : classes) {
+        const Key key = kv.first;
+        const int64_t nv = (int64_t)kv.second.size();
+        const int threads = key.C == 1 ? tn.threads_c1 : (key.C == 2 ? tn.threads_c2 : tn.threads_c4);
+        const int tile_w = key.C * threads;
+        const int rows_cap = key.NW * (32 / key.C);
+        const size_t smem = (size_t)rows_cap * tile_w + 16;
+        if (smem > (size_t)dp.smem_optin) {
+            rc = fail(BGD_ERR_UNSUPPORTED, "median (column-plane): tile of %d rows x %d bytes exceeds shared memory", rows_cap, tile_w);
+            break;
+        }
+        prm.out = d_out;
+        prm.vid_row0 = d_row0 + pos;
+        prm.vid_T = d_T + pos;
+        prm.vid_out = d_outi + pos;
+        prm.N = N;
+        prm.tiles_per_video = (int32_t)((N + tile_w - 1) / tile_w);
+        prm.num_tiles = nv * prm.tiles_per_video;
+        prm.rows_cap = rows_cap;
+        if (key.C == 1) rc = colplane::launch_c1(key.NW, key.even != 0, prm, threads, dp.sm_count, smem, stream);
+        else if (key.C == 2) rc = colplane::launch_c2(key.NW, key.even != 0, prm, threads, dp.sm_count, smem, stream);
+        else rc = colplane::launch_c4(key.NW, key.even != 0, prm, threads, dp.sm_count, smem, stream);
+        if (rc) break;
+        pos += nv;
+    }
+    const int rc2 = ws.release(stream);
+    return rc ? rc : rc2;
+}
+
+}  // namespace bgd

@@ -46,7 +46,8 @@ typedef enum bgd_status {
 /* Median kernel variants (for differential testing; AUTO is the product path). */
 #define BGD_MEDIAN_AUTO      0
 #define BGD_MEDIAN_SWAR      1   /* thread-per-4-columns byte-SIMD binary search; any T, any N */
-#define BGD_MEDIAN_BITSLICED 2   /* TMA-staged bit-sliced radix select; needs N % 16 == 0      */
+#define BGD_MEDIAN_BITSLICED 2   /* TMA-staged cooperative bit-sliced select; needs N % 16 == 0 */
+#define BGD_MEDIAN_COLPLANE  3   /* TMA-staged thread-per-column bit-plane select (AUTO's choice) */
 
 /* ---- library / device ------------------------------------------------------------------ */
 

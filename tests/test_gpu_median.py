@@ -35,7 +35,10 @@ def _gpu_median(ops, frames_np):
     return torch.ops.bgdebias.temporal_median(t).cpu().numpy()
 
 
-@pytest.mark.parametrize("variant", ["auto", "swar", "bitsliced"])
+VARIANTS = {"auto": 0, "swar": 1, "bitsliced": 2, "colplane": 3}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("name", CASES)
 def test_golden_reference_outputs(bgd, name, variant):
     ops, cabi = bgd
@@ -43,8 +46,8 @@ def test_golden_reference_outputs(bgd, name, variant):
     interval, max_frames = (int(v) for v in _NPZ[name + "/params"])
     used = frames[mo.select_frame_indices(len(frames), interval, max_frames)]
     N = int(np.prod(used.shape[1:]))
-    cabi.set_median_variant({"auto": 0, "swar": 1, "bitsliced": 2}[variant])
-    if variant == "bitsliced" and N % 16 != 0:
+    cabi.set_median_variant(VARIANTS[variant])
+    if variant in ("bitsliced", "colplane") and N % 16 != 0:
         with pytest.raises(cabi.BgdError):
             _gpu_median(ops, used)
         return
@@ -53,16 +56,16 @@ def test_golden_reference_outputs(bgd, name, variant):
 
 
 T_VALUES = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 96, 100, 127, 128, 129,
-            179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 527, 528, 576]
+            179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 527, 528, 543, 544, 576]
 
 
-@pytest.mark.parametrize("variant", ["swar", "bitsliced"])
+@pytest.mark.parametrize("variant", ["swar", "bitsliced", "colplane"])
 @pytest.mark.parametrize("T", T_VALUES)
 def test_random_all_T(bgd, T, variant):
     ops, cabi = bgd
-    if variant == "bitsliced" and T > 528:
-        pytest.skip("bit-sliced variant holds at most 528 rows per CTA; AUTO falls back to the generic variant")
-    cabi.set_median_variant({"swar": 1, "bitsliced": 2}[variant])
+    if (variant == "bitsliced" and T > 528) or (variant == "colplane" and T > 544):
+        pytest.skip("the TMA variants hold at most ~500 rows per thread group; AUTO falls back to the generic variant")
+    cabi.set_median_variant(VARIANTS[variant])
     rng = np.random.default_rng(1000 + T)
     N = 16 * int(rng.integers(1, 90))                     # ragged tile tails
     fr = rng.integers(0, 256, (T, N), dtype=np.uint8)
@@ -95,7 +98,7 @@ def test_patterns(bgd, pattern, T):
     else:
         fr = np.zeros((T, N), np.uint8)
     exp = mo.temporal_median_np(fr)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         cabi.set_median_variant(variant)
         np.testing.assert_array_equal(_gpu_median(ops, fr), exp)
 
@@ -120,7 +123,7 @@ def test_varlen_mixed_lengths(bgd):
     fr = rng.integers(0, 256, (int(offs[-1]), N), dtype=np.uint8)
     exp = c_oracle.temporal_median_varlen(fr, offs)
     d = torch.from_numpy(fr).cuda()
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         cabi.set_median_variant(variant)
         got = torch.ops.bgdebias.temporal_median_varlen(d, torch.from_numpy(offs)).cpu().numpy()
         np.testing.assert_array_equal(got, exp)

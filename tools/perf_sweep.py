@@ -26,8 +26,18 @@ for case in cases:
     rows = int(offs[-1])
     fr = torch.randint(0, 256, (rows, N), dtype=torch.uint8, device="cuda")
     by = (rows + V) * N
-    _cabi.set_median_variant(0)
-    for R, TH, C in itertools.product(Rs, THs, Cs):
+    for var in [int(v) for v in os.environ.get("VARIANTS", "3").split(",")]:
+        if var == 2: continue
+        _cabi.set_median_variant(var)
+        for thr in [int(v) for v in os.environ.get("COLTHR", "128,256").split(",")]:
+            os.environ["BGD_COL_THREADS_C2"] = str(thr); os.environ["BGD_COL_THREADS_C4"] = str(thr)
+            try:
+                ms = run(fr, offs)
+                print(f"T={case:>5s} variant={var} col_threads={thr}: {ms:7.3f} ms {by/ms/1e6:7.1f} GB/s {rows/ms/1e3:6.2f} Mframes/s", flush=True)
+            except Exception as e:
+                print(f"T={case} variant={var} thr={thr}: ERROR {e}", flush=True)
+    _cabi.set_median_variant(2)
+    for R, TH, C in (itertools.product(Rs, THs, Cs) if "2" in os.environ.get("VARIANTS", "3").split(",") else []):
         os.environ["BGD_MEDIAN_TARGET_R"] = str(R); os.environ["BGD_MEDIAN_TARGET_THREADS"] = str(TH); os.environ["BGD_MEDIAN_CTAS_PER_SM"] = str(C)
         try:
             ms = run(fr, offs)
