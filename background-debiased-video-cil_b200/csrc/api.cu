@@ -392,7 +392,7 @@ int bgd_bgmix_blend_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, in
 {
     DeviceProps dp;
     if (int rc = current_device_props(&dp)) return rc;
-    return launch_bgmix(d_fg, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
+    return launch_bgmix(d_fg, nullptr, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
                         h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -404,8 +404,21 @@ int bgd_bgmix_blend_u8pool_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_
 {
     DeviceProps dp;
     if (int rc = current_device_props(&dp)) return rc;
-    return launch_bgmix(d_fg, B, T, H, W, d_bg_pool, true, P, Hb, Wb, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
+    return launch_bgmix(d_fg, nullptr, B, T, H, W, d_bg_pool, true, P, Hb, Wb, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
                         h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_bgmix_blend_normfg_f32(const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W,
+                               const void *d_bg_pool, int pool_is_u8, int64_t P, int64_t Hb, int64_t Wb,
+                               const int32_t *d_bg_idx, const int32_t *d_top, const int32_t *d_left,
+                               const uint8_t *d_apply, const float *h_bg_mean, const float *h_bg_std, double alpha,
+                               int layout, float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    if (!d_fg_norm) return fail(BGD_ERR_INVALID, "bgmix: null foreground");
+    return launch_bgmix(nullptr, d_fg_norm, B, T, H, W, d_bg_pool, pool_is_u8 != 0, P, Hb, Wb, d_bg_idx, d_top, d_left,
+                        d_apply, nullptr, h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t H, int64_t W, const float *d_bg_pool,
@@ -441,7 +454,7 @@ int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t 
     std::memcpy(hp + o + (size_t)B * 12, h_apply, (size_t)B);
     BGD_CUDA_TRY(cudaMemcpyAsync(dp_, hp, o + (size_t)B * 13, cudaMemcpyHostToDevice, s));
     const int32_t *d_idx = reinterpret_cast<const int32_t *>(dp_ + o);
-    if (int rc = launch_bgmix(dp_, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_idx, d_idx + B, d_idx + 2 * B,
+    if (int rc = launch_bgmix(dp_, nullptr, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_idx, d_idx + B, d_idx + 2 * B,
                               dp_ + o + (size_t)B * 12, d_fg_lut, h_bg_mean, h_bg_std, alpha, layout, d_out, s))
         return rc;
     if (h_checksum) {

@@ -52,7 +52,7 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
                            uint8_t *d_out, cudaStream_t stream);
 bool median_colplane_supports(int64_t T_max, int64_t N);
 
-int launch_bgmix(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W, const void *d_pool,
+int launch_bgmix(const uint8_t *d_fg, const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W, const void *d_pool,
                  bool pool_is_u8, int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx,
                  const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
                  const float *d_lut, const float *h_mean, const float *h_std, double alpha,

@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(kThreads) bgmix_kernel(const MixParams prm)
         const int64_t y = p0 / prm.W, x = p0 - y * prm.W;
         int64_t idx = prm.bg_idx[b];
         idx = idx < 0 ? 0 : (idx >= prm.P ? prm.P - 1 : idx);               // host validates; clamp = no OOB
-        const PoolT *pb = static_cast<const PoolT *>(prm.pool) +
-                          ((idx * 3) * prm.Hb + (prm.top[b] + y)) * prm.Wb + prm.left[b] + x;
+        const int64_t top = min(max((int64_t)prm.top[b], (int64_t)0), prm.Hb - prm.H);     // host validates; clamp = no OOB
+        const int64_t left = min(max((int64_t)prm.left[b], (int64_t)0), prm.Wb - prm.W);
+        const PoolT *pb = static_cast<const PoolT *>(prm.pool) + ((idx * 3) * prm.Hb + (top + y)) * prm.Wb + left + x;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -105,6 +106,51 @@ __global__ void __launch_bounds__(kThreads) bgmix_kernel(const MixParams prm)
     }
 }
 
+// Foreground already normalised (fp32 [B][T][3][H][W], what the reference's pipeline hands to
+// _mix_background): out = fg * f32(1 - alpha) + bg_norm * f32(alpha), or a plain copy when the
+// sample is not mixed.  One thread: VEC adjacent pixels of one (sample, channel), all T frames.
+template <typename PoolT, int VEC>
+__global__ void __launch_bounds__(kThreads) bgmix_normfg_kernel(const MixParams prm, const float *__restrict__ fgn)
+{
+    const int64_t b = blockIdx.z, c = blockIdx.y;
+    const int64_t HW = prm.H * prm.W;
+    const int64_t p0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+    if (p0 >= HW) return;
+    const bool apply = prm.apply[b] != 0;
+    float g[VEC];
+    if (apply) {
+        const int64_t y = p0 / prm.W, x = p0 - y * prm.W;
+        int64_t idx = prm.bg_idx[b];
+        idx = idx < 0 ? 0 : (idx >= prm.P ? prm.P - 1 : idx);
+        const int64_t top = min(max((int64_t)prm.top[b], (int64_t)0), prm.Hb - prm.H);
+        const int64_t left = min(max((int64_t)prm.left[b], (int64_t)0), prm.Wb - prm.W);
+        const PoolT *pb = static_cast<const PoolT *>(prm.pool) + ((idx * 3 + c) * prm.Hb + (top + y)) * prm.Wb + left + x;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            g[i] = __fmul_rn(__fdiv_rn(__fsub_rn(load_bg(pb + i), prm.mean[c]), prm.std[c]), prm.w_bg);
+    }
+    const float *src = fgn + (b * prm.T * 3 + c) * HW + p0;
+    float *out = prm.out + b * prm.T * 3 * HW + c * prm.out_stride_c + p0;
+    for (int64_t t = 0; t < prm.T; ++t) {
+        float f[VEC];
+        if (VEC == 4) {
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(src + t * 3 * HW));
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) f[i] = __ldcs(src + t * 3 * HW + i);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) f[i] = apply ? __fadd_rn(__fmul_rn(f[i], prm.w_fg), g[i]) : f[i];
+        float *dst = out + t * prm.out_stride_t;
+        if (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(f[0], f[1], f[2], f[3]));
+        else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) __stcs(dst + i, f[i]);
+        }
+    }
+}
+
 __global__ void sum_f32_kernel(const float *__restrict__ x, int64_t n, double *__restrict__ out)
 {
     double acc = 0.0;
@@ -123,7 +169,7 @@ __global__ void sum_f32_kernel(const float *__restrict__ x, int64_t n, double *_
 
 }  // namespace
 
-int launch_bgmix(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W, const void *d_pool,
+int launch_bgmix(const uint8_t *d_fg, const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W, const void *d_pool,
                  bool pool_is_u8, int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx,
                  const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
                  const float *d_lut, const float *h_mean, const float *h_std, double alpha, int layout,
@@ -131,7 +177,7 @@ int launch_bgmix(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W
 {
     if (B < 0 || T < 0 || H < 0 || W < 0) return fail(BGD_ERR_INVALID, "bgmix: negative size");
     if (B == 0 || T == 0 || H == 0 || W == 0) return BGD_OK;
-    if (!d_fg || !d_out || !d_lut || !d_apply) return fail(BGD_ERR_INVALID, "bgmix: null pointer");
+    if ((!d_fg && !d_fg_norm) || !d_out || (!d_lut && !d_fg_norm) || !d_apply) return fail(BGD_ERR_INVALID, "bgmix: null pointer");
     if (!h_mean || !h_std) return fail(BGD_ERR_INVALID, "bgmix: null mean/std");
     if (P > 0 && (!d_pool || !d_bg_idx || !d_top || !d_left)) return fail(BGD_ERR_INVALID, "bgmix: null pool argument");
     if (P > 0 && (Hb < H || Wb < W))
@@ -151,6 +197,21 @@ int launch_bgmix(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W
     if (layout == BGD_LAYOUT_NTCHW) { prm.out_stride_t = 3 * HW; prm.out_stride_c = HW; }
     else                            { prm.out_stride_t = HW;     prm.out_stride_c = T * HW; }
 
+    if (d_fg_norm) {
+        const bool v4 = (W % 4 == 0) && reinterpret_cast<uintptr_t>(d_fg_norm) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
+        const int vw = v4 ? 4 : 1;
+        dim3 grid((unsigned)((HW / vw + kThreads - 1) / kThreads), 3u, (unsigned)B);
+        if (pool_is_u8) {
+            if (v4) bgmix_normfg_kernel<uint8_t, 4><<<grid, kThreads, 0, stream>>>(prm, d_fg_norm);
+            else    bgmix_normfg_kernel<uint8_t, 1><<<grid, kThreads, 0, stream>>>(prm, d_fg_norm);
+        } else {
+            if (v4) bgmix_normfg_kernel<float, 4><<<grid, kThreads, 0, stream>>>(prm, d_fg_norm);
+            else    bgmix_normfg_kernel<float, 1><<<grid, kThreads, 0, stream>>>(prm, d_fg_norm);
+        }
+        count_launch();
+        BGD_CUDA_TRY(cudaGetLastError());
+        return BGD_OK;
+    }
     const bool vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(d_fg) % 4 == 0) &&
                      (reinterpret_cast<uintptr_t>(d_out) % 16 == 0);
     const int px = vec ? 4 : 1;

@@ -1,0 +1,199 @@
+"""Drop-in for ``cil_tools/extract_background.py`` of the reference: same CLI flags, same function
+signatures, same output files (``<output_dir>/<video name>.jpg``); the per-pixel temporal median
+runs on the GPU (``torch.ops.bgdebias.temporal_median*``), everything else stays on the host.
+
+    python -m bgdebias_b200.extract_background --video_dir D --output_dir O --from_video \
+        [--glob_pattern '*'] [--num_workers 4] [--image_suffix .jpg] [--interval 1] \
+        [--max_frames 500] [--size 256] [--method tmf] [--avg_method median]
+
+``--num_workers`` keeps its meaning "number of parallel shards of the video list"; every shard is
+one process bound to one GPU (shard i -> GPU i mod #GPUs).  Additional, optional flags:
+``--decode_threads`` (host decoder threads per shard) and ``--slab_mb`` (pinned staging slab size).
+
+Behaviour kept from the reference on purpose
+* frames are kept while ``len(frames) <= max_frames``: up to ``max_frames + 1`` frames (:52);
+* a frame is kept when ``count % interval == 0`` where ``count`` counts decoded frames (:54-60);
+* ``--size`` is accepted and unused, backgrounds are written at native resolution (:27,57);
+* videos whose output already exists are skipped (:119-126).
+Behaviour NOT kept: the image-folder branch of the reference raises ``ValueError`` on the first
+readable image (``if img:`` on an ndarray, :67-68); here it reads the images as evidently intended.
+"""
+from __future__ import annotations
+
+import argparse
+import pathlib
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from typing import List
+
+import cv2
+import numpy as np
+import torch
+
+from . import shard as _shard
+from .staging import FrameStager
+
+
+def parse_args(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--video_dir', required=True)
+    parser.add_argument('--glob_pattern', default='*')
+    parser.add_argument('--output_dir', required=True)
+    parser.add_argument('--num_workers', type=int, default=4)
+    parser.add_argument('--from_video', action='store_true')
+    parser.add_argument('--image_suffix', default='.jpg')
+    parser.add_argument('--interval', type=int, default=1)
+    parser.add_argument('--max_frames', type=int, default=500)
+    parser.add_argument('--size', type=int, default=256)
+    parser.add_argument('--method', default='tmf')
+    parser.add_argument('--avg_method', default='median')
+    # extensions
+    parser.add_argument('--decode_threads', type=int, default=4)
+    parser.add_argument('--slab_mb', type=int, default=512)
+    return parser.parse_args(argv)
+
+
+def read_frames(data_path: pathlib.Path, from_video: bool, interval: int, max_frames: int) -> List[np.ndarray]:
+    """The frame-collection loops of the reference (extract_background.py:48-71)."""
+    frames = []
+    count = 0
+    if from_video:
+        cap = cv2.VideoCapture(str(data_path))
+        while cap.isOpened() and len(frames) <= max_frames:
+            ret, frame_ = cap.read()
+            if count % interval == 0:
+                if ret:
+                    frames.append(frame_)
+                else:
+                    break
+            elif not ret:
+                break              # end of stream on a skipped position: the next kept read would fail too
+            count += 1
+        cap.release()
+    else:
+        for img_f in sorted(pathlib.Path(data_path).glob('*')):
+            if len(frames) > max_frames:
+                break
+            if count % interval == 0:
+                img = cv2.imread(str(img_f))
+                if img is not None:
+                    frames.append(img)
+            count += 1
+    return frames
+
+
+def temporal_median_frames(frames: List[np.ndarray], device=0) -> np.ndarray:
+    """``np.median(frames, axis=0).astype(np.uint8)`` on the GPU for a list of host frames, through the
+    host-buffer entry point of the C ABI (gathers the separately allocated frames into pinned memory)."""
+    import ctypes
+    from . import _cabi
+    if len(frames) == 0:
+        raise ValueError("median of zero frames")        # reference: nan median, cv2.imwrite raises
+    shape = frames[0].shape
+    arrs = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames]
+    for a in arrs:
+        if a.shape != shape:
+            raise ValueError("all frames must have the same shape")
+    N = int(np.prod(shape))
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    out = np.empty(shape, np.uint8)
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    _cabi.check(_cabi.lib().bgd_temporal_median_u8_host(ptrs, len(arrs), N, out.ctypes.data,
+                                                        dev.index if dev.index is not None else 0))
+    return out
+
+
+def bg_extraction_tmf(data_path: pathlib.Path, dest: pathlib.Path,
+                      from_video: bool, interval: int, max_frames: int, *args, **kwargs):
+    """extract background using median temporal filtering -- same signature and return value as
+    the reference (extract_background.py:42-75): writes ``dest`` and returns the ``[H,W,3]`` uint8
+    median frame.  ``device=`` (keyword) selects the GPU."""
+    frames = read_frames(pathlib.Path(data_path), from_video, interval, max_frames)
+    median_frame = temporal_median_frames(frames, kwargs.get('device', 0))
+    cv2.imwrite(str(dest), median_frame)
+    return median_frame
+
+
+def sim_cam_motion_bg_extract(data_path, dest, from_video, interval, max_frames, avg_method):
+    """The reference's simulated-camera-motion variant (extract_background.py:78-99) is a float
+    NaN-masked median over random crops; it is outside this path's scope."""
+    raise NotImplementedError("--method sim_cam is not part of the B200 path; use the reference for it")
+
+
+def bg_extract_multiple(paths: List[pathlib.Path], output_dir: pathlib.Path, from_video: bool,
+                        interval: int, max_frames: int, process_id: int, method, avg_method: int,
+                        device=None, decode_threads: int = 4, slab_mb: int = 512):
+    """Same role and leading arguments as the reference (extract_background.py:102-109).  For the
+    ``tmf`` method the videos of this shard are decoded by a thread pool into a pinned slab and
+    reduced many-per-launch; any other ``method`` callable is invoked video by video like the reference."""
+    output_dir = pathlib.Path(output_dir)
+    if method is not bg_extraction_tmf:
+        for data_path in paths:
+            method(data_path, (output_dir / data_path.name).with_suffix('.jpg'), from_video, interval, max_frames,
+                   avg_method)
+        return []
+    if device is None:
+        device = _shard.device_for(process_id, torch.cuda.device_count())
+    dev = torch.device(f"cuda:{device}" if isinstance(device, int) else device)
+    torch.cuda.set_device(dev)
+    failures = []
+
+    def write(tag, bg):
+        cv2.imwrite(str(tag), bg)
+
+    stager = FrameStager(write, dev, slab_mb)
+
+    def decode(p):
+        try:
+            return p, read_frames(p, from_video, interval, max_frames), None
+        except Exception as e:  # keep going, report at the end
+            return p, [], e
+
+    with ThreadPoolExecutor(max_workers=max(1, decode_threads)) as pool:
+        for p, frames, err in pool.map(decode, paths):
+            if err is not None or not frames:
+                failures.append((str(p), repr(err) if err else "no frames decoded"))
+                continue
+            stager.add_video(frames, (output_dir / p.name).with_suffix('.jpg'))
+    stager.flush()
+    return failures
+
+
+def _shard_entry(rank, shard_paths, output_dir, from_video, interval, max_frames, method_name, avg_method,
+                 decode_threads, slab_mb):
+    method = bg_extraction_tmf if method_name == 'tmf' else sim_cam_motion_bg_extract
+    failures = bg_extract_multiple(shard_paths, pathlib.Path(output_dir), from_video, interval, max_frames, rank,
+                                   method, avg_method, None, decode_threads, slab_mb)
+    if failures:
+        raise RuntimeError(f"{len(failures)} videos failed in shard {rank}: {failures[:5]}")
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    output_dir = pathlib.Path(args.output_dir)
+    output_dir.mkdir(exist_ok=True)
+    video_dir = pathlib.Path(args.video_dir)
+
+    # check duplicated background (extract_background.py:118-126)
+    video_paths = set(video_dir.glob(args.glob_pattern))
+    extracted = [p_ for p_ in video_paths if (output_dir / p_.name).with_suffix(args.image_suffix).exists()]
+    video_paths = sorted(video_paths.difference(extracted))
+    print('Found {} backgrounds'.format(len(extracted)))
+    print('Extracting background from {} videos'.format(len(video_paths)))
+
+    if args.method not in ('tmf', 'sim_cam'):
+        raise ValueError
+    if args.avg_method == 'median':
+        avg_method = 0
+    elif args.avg_method == 'mean':
+        avg_method = 1
+    else:
+        raise ValueError
+
+    splits = _shard.contiguous_splits(video_paths, args.num_workers)
+    _shard.run_shards(_shard_entry, splits, str(output_dir), args.from_video, args.interval, args.max_frames,
+                      args.method, avg_method, args.decode_threads, args.slab_mb)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])

@@ -146,3 +146,41 @@ def make_fg_lut(mean: Sequence[float], std: Sequence[float], device=None) -> tor
     d32 = x[None, :] - mean64.to(torch.float32)[:, None]
     lut = (d32.to(torch.float64) * (1.0 / std64)[:, None]).to(torch.float32)
     return lut.to(device) if device is not None else lut
+
+
+@torch.library.custom_op("bgdebias::bgmix_blend_normfg", mutates_args=(), device_types="cuda")
+def bgmix_blend_normfg(fg_norm: torch.Tensor, bg_pool: torch.Tensor, bg_idx: torch.Tensor, top: torch.Tensor,
+                       left: torch.Tensor, apply: torch.Tensor, bg_mean: torch.Tensor, bg_std: torch.Tensor,
+                       alpha: float, layout: str) -> torch.Tensor:
+    """Blend for a foreground that is already normalised: fp32 [B, T, 3, H, W] (the ``imgs`` the
+    reference's pipeline produces, libs/loader/comix_loader.py:142)."""
+    _require(fg_norm.dtype == torch.float32 and fg_norm.dim() == 5 and fg_norm.shape[2] == 3,
+             "bgmix_blend_normfg: fg_norm must be float32 [B, T, 3, H, W]")
+    _require(bg_pool.dim() == 4 and bg_pool.shape[1] == 3 and bg_pool.dtype in (torch.float32, torch.uint8),
+             "bgmix_blend_normfg: bg_pool must be float32 or uint8 [P, 3, Hb, Wb]")
+    _require(layout in _cabi.LAYOUTS, f"bgmix_blend_normfg: layout must be one of {sorted(_cabi.LAYOUTS)}")
+    B, T, _, H, W = fg_norm.shape
+    P, _, Hb, Wb = bg_pool.shape
+    dev = fg_norm.device
+    for name, t, dt in (("bg_idx", bg_idx, torch.int32), ("top", top, torch.int32), ("left", left, torch.int32),
+                        ("apply", apply, torch.uint8)):
+        _require(t.dtype == dt and t.dim() == 1 and t.shape[0] == B and t.device == dev,
+                 f"bgmix_blend_normfg: {name} must be {dt} [B] on {dev}")
+    _require(bg_pool.device == dev, "bgmix_blend_normfg: bg_pool must be on the same device as fg_norm")
+    fg_norm, bg_pool = fg_norm.contiguous(), bg_pool.contiguous()
+    bg_idx, top, left, apply = (x.contiguous() for x in (bg_idx, top, left, apply))
+    shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().bgd_bgmix_blend_normfg_f32(
+            fg_norm.data_ptr(), B, T, H, W, bg_pool.data_ptr(), int(bg_pool.dtype == torch.uint8), P, Hb, Wb,
+            bg_idx.data_ptr(), top.data_ptr(), left.data_ptr(), apply.data_ptr(), _host3(bg_mean, "bg_mean"),
+            _host3(bg_std, "bg_std"), float(alpha), _cabi.LAYOUTS[layout], out.data_ptr(), _stream_ptr(dev)))
+    return out
+
+
+@bgmix_blend_normfg.register_fake
+def _(fg_norm, bg_pool, bg_idx, top, left, apply, bg_mean, bg_std, alpha, layout):
+    B, T, _, H, W = fg_norm.shape
+    shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
+    return fg_norm.new_empty(shape)

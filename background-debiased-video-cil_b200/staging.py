@@ -1,0 +1,114 @@
+"""Video-to-GPU staging: pinned double buffer between the host decoder and the median kernel.
+
+The reference keeps a Python list of decoded frames per video and calls ``np.median`` on it
+(cil_tools/extract_background.py:48-73).  Here decoded frames are written straight into a pinned
+slab that holds several whole videos back to back (``[sum T, N]`` uint8 plus the offsets table);
+when a slab is full it is copied to the device on its own stream, reduced with one
+``temporal_median_varlen`` launch, and the ``[V, N]`` backgrounds are copied back -- while the
+decoder is already filling the other slab.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+class _Slab:
+    def __init__(self, nbytes: int, device: torch.device):
+        self.host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.stream = torch.cuda.Stream(device)
+        self.done = torch.cuda.Event()
+        self.reset()
+
+    def reset(self):
+        self.used = 0
+        self.N = None
+        self.offsets: List[int] = [0]
+        self.tags: list = []
+        self.shapes: list = []
+        self.out_host: Optional[torch.Tensor] = None
+        self.pending = False
+
+
+class FrameStager:
+    """``add_video(frames, tag)`` queues one decoded video (list/array of equal-shaped uint8 frames);
+    ``on_result(tag, background_ndarray)`` is called for every video once its median is back on the
+    host.  Call :meth:`flush` at the end."""
+
+    def __init__(self, on_result: Callable, device="cuda", slab_mb: int = 512):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FrameStager needs a CUDA device: there is no CPU path")
+        self.on_result = on_result
+        self.slab_bytes = int(slab_mb) << 20
+        self.slabs: List[Optional[_Slab]] = [None, None]
+        self.cur = 0
+
+    def _slab(self, i: int, need: int) -> _Slab:
+        s = self.slabs[i]
+        if s is None or s.host.numel() < need:
+            if s is not None and s.pending:
+                self._drain(i)
+            self.slabs[i] = s = _Slab(max(self.slab_bytes, need), self.device)
+        return s
+
+    def add_video(self, frames: Sequence[np.ndarray], tag) -> None:
+        T = len(frames)
+        if T == 0:
+            # reference: np.median([]) -> nan -> cv2.imwrite raises (extract_background.py:73-74)
+            raise ValueError(f"{tag}: no frames decoded")
+        shape = tuple(frames[0].shape)
+        N = int(np.prod(shape))
+        need = T * N
+        slab = self._slab(self.cur, need)
+        if slab.pending:
+            self._drain(self.cur)
+        if slab.used and (slab.N != N or slab.used + need > slab.host.numel()):
+            self._submit(self.cur)
+            self.cur ^= 1
+            slab = self._slab(self.cur, need)
+            if slab.pending:
+                self._drain(self.cur)
+        slab.N = N
+        view = slab.host[slab.used:slab.used + need].view(T, N).numpy()
+        for t, f in enumerate(frames):
+            if tuple(f.shape) != shape or f.dtype != np.uint8:
+                raise ValueError(f"{tag}: frame {t} differs in shape or dtype")
+            view[t] = f.reshape(-1)
+        slab.used += need
+        slab.offsets.append(slab.offsets[-1] + T)
+        slab.tags.append(tag)
+        slab.shapes.append(shape)
+
+    def _submit(self, i: int) -> None:
+        slab = self.slabs[i]
+        if slab is None or not slab.tags:
+            return
+        V, N = len(slab.tags), slab.N
+        rows = slab.offsets[-1]
+        with torch.cuda.stream(slab.stream):
+            slab.dev[:slab.used].copy_(slab.host[:slab.used], non_blocking=True)
+            out = torch.ops.bgdebias.temporal_median_varlen(slab.dev[:slab.used].view(rows, N),
+                                                            torch.tensor(slab.offsets, dtype=torch.int64))
+            slab.out_host = torch.empty((V, N), dtype=torch.uint8, pin_memory=True)
+            slab.out_host.copy_(out, non_blocking=True)
+            slab.done.record(slab.stream)
+        slab.pending = True
+
+    def _drain(self, i: int) -> None:
+        slab = self.slabs[i]
+        if slab is None or not slab.pending:
+            return
+        slab.done.synchronize()
+        res = slab.out_host.numpy()
+        for v, (tag, shape) in enumerate(zip(slab.tags, slab.shapes)):
+            self.on_result(tag, res[v].reshape(shape).copy())
+        slab.reset()
+
+    def flush(self) -> None:
+        self._submit(self.cur)
+        for i in (self.cur ^ 1, self.cur):
+            self._drain(i)

@@ -135,6 +135,17 @@ int bgd_bgmix_blend_u8pool_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_
                                const float *h_bg_mean, const float *h_bg_std, double alpha,
                                int layout, float *d_out, void *stream);
 
+/* Foreground already normalised: d_fg_norm fp32 [B][T][3][H][W] is the `imgs` tensor the reference's
+ * pipeline hands to _mix_background (libs/loader/comix_loader.py:142); no table is involved.
+ * out = fg * f32(1 - alpha) + bg_norm * f32(alpha) where apply != 0, a copy elsewhere.
+ * d_bg_pool is fp32 (pool_is_u8 == 0) or uint8 (pool_is_u8 != 0) [P][3][Hb][Wb]. */
+int bgd_bgmix_blend_normfg_f32(const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W,
+                               const void *d_bg_pool, int pool_is_u8, int64_t P, int64_t Hb,
+                               int64_t Wb, const int32_t *d_bg_idx, const int32_t *d_top,
+                               const int32_t *d_left, const uint8_t *d_apply,
+                               const float *h_bg_mean, const float *h_bg_std, double alpha,
+                               int layout, float *d_out, void *stream);
+
 /* Host-buffer form: foreground batch and per-sample parameters live in host memory (what a
  * DataLoader collate hands over), the pool and the LUT are device resident.  Copies the inputs
  * in, blends, leaves the training tensor in d_out (device) and returns after the stream is

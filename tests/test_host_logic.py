@@ -1,0 +1,147 @@
+"""CPU tests of the host-side mirror: shard split, frame selection, RNG draw order, the LUT, pool
+geometry, and the multi-rank pool all-gather (gloo, world_size 2)."""
+import os
+import pathlib
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bgmix_oracle as bo, median_oracle as mo
+
+
+def test_contiguous_splits_match_reference():
+    from bgdebias_b200 import shard
+    for n, w in [(10, 4), (3, 4), (0, 2), (13320, 8), (7, 7), (8, 3)]:
+        ours = shard.contiguous_splits(list(range(n)), w)
+        ref = mo.reference_contiguous_splits(n, w)
+        assert [list(r) for r in ref] == ours
+        assert sum(len(s) for s in ours) == n
+    assert shard.rank_slice(list(range(10)), 3, 4) == [9]
+    assert shard.device_for(5, 4) == 1
+    with pytest.raises(RuntimeError):
+        shard.device_for(0, 0)
+
+
+def _write_ffv1(path, frames):
+    import cv2
+    T, H, W, _ = frames.shape
+    wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"FFV1"), 25, (W, H))
+    for f in frames:
+        wr.write(f)
+    wr.release()
+
+
+@pytest.mark.parametrize("n,interval,max_frames", [(20, 1, 4), (40, 2, 5), (50, 3, 500), (9, 1, 500), (9, 4, 0)])
+def test_read_frames_selection_matches_oracle(tmp_path, n, interval, max_frames):
+    """read_frames keeps exactly the frames the reference's loop keeps (extract_background.py:52-60)."""
+    from bgdebias_b200 import extract_background as eb
+    fr = np.random.default_rng(n).integers(0, 256, (n, 16, 24, 3), dtype=np.uint8)
+    vid = tmp_path / "v.avi"
+    _write_ffv1(vid, fr)
+    got = eb.read_frames(vid, True, interval, max_frames)
+    idx = mo.select_frame_indices(n, interval, max_frames)
+    assert len(got) == len(idx)
+    for g, i in zip(got, idx):
+        np.testing.assert_array_equal(g, fr[i])
+
+
+def test_read_frames_image_folder(tmp_path):
+    import cv2
+    from bgdebias_b200 import extract_background as eb
+    fr = np.random.default_rng(1).integers(0, 256, (7, 8, 8, 3), dtype=np.uint8)
+    for t, f in enumerate(fr):
+        cv2.imwrite(str(tmp_path / f"img_{t + 1:05}.png"), f)
+    got = eb.read_frames(tmp_path, False, 2, 500)
+    assert len(got) == 4
+    np.testing.assert_array_equal(got[1], fr[2])
+
+
+def test_cli_flags_are_the_reference_flags():
+    from bgdebias_b200 import extract_background as eb
+    a = eb.parse_args(["--video_dir", "v", "--output_dir", "o"])
+    assert (a.glob_pattern, a.num_workers, a.from_video, a.image_suffix, a.interval, a.max_frames, a.size, a.method,
+            a.avg_method) == ('*', 4, False, '.jpg', 1, 500, 256, 'tmf', 'median')
+
+
+def test_fg_lut_bitwise_equals_oracle():
+    from bgdebias_b200 import ops
+    for mean, std in [(bo.DEFAULT_MEAN, bo.DEFAULT_STD), ((10.5, 200.25, 0.0), (1.0, 33.3, 255.0))]:
+        np.testing.assert_array_equal(ops.make_fg_lut(mean, std).numpy().view(np.uint32), bo.fg_lut(mean, std).view(np.uint32))
+
+
+def test_pool_geometry_and_draw_order():
+    from bgdebias_b200 import comix_loader as cl, pool
+    for h, w, s in [(240, 320, 256), (240, 427, 256), (320, 240, 256), (256, 256, 256), (90, 120, 36)]:
+        assert pool.resized_hw(h, w, s) == bo.resized_hw(h, w, s)
+        assert tuple(pool.resize_like_reference(torch.zeros(3, h, w), s).shape[1:]) == bo.resized_hw(h, w, s)
+    torch.manual_seed(5)
+    a = (int(torch.randint(9, (1,)).item()),) + cl.draw_crop(256, 341, (224, 224))
+    torch.manual_seed(5)
+    assert a == bo.draw_bg_params(9, 256, 341, (224, 224))
+    torch.manual_seed(5)
+    st = torch.get_rng_state()
+    assert cl.draw_crop(224, 224, (224, 224)) == (0, 0)          # nothing drawn when sizes match
+    assert torch.equal(st, torch.get_rng_state())
+    with pytest.raises(ValueError):
+        cl.draw_crop(100, 300, (224, 224))
+
+
+def test_dataset_pool_modes_without_gpu(tmp_path):
+    """Pool assembly (comix_loader.py:84-103) needs no device."""
+    from bgdebias_b200 import comix_loader as cl
+    bg = tmp_path / "bg"
+    bg.mkdir()
+    for n in ("a", "b", "zz"):
+        (bg / f"{n}.jpg").write_bytes(b"x")
+    infos = [dict(frame_dir=f"/d/{n}", total_frames=3, label=0) for n in ("a", "b", "c")]
+    ident = lambda r: r
+    ds = cl.BackgroundMixDataset(infos, ident, bg_dir=str(bg), extract_bg_if_not_found=False)
+    assert [pathlib.Path(p).name for p in ds.bg_files] == ["a.jpg", "b.jpg"]
+    ds2 = cl.BackgroundMixDataset(infos, ident, bg_dir=str(bg), map_bg_to_video=False, merge_bg_files=False)
+    assert sorted(pathlib.Path(p).name for p in ds2.bg_files) == ["a.jpg", "b.jpg", "zz.jpg"]
+    ds3 = cl.BackgroundMixDataset(infos, ident, bg_dir=str(bg), back_ground_from_bg_dir=False)
+    assert ds3.bg_files == []
+    assert ds.merge_bg_files is True and ds.test_mode is False and len(ds.video_infos) == 3
+    # gate: with_randAug and randAug=True -> untouched, bg_idx -1, no GPU needed
+    ds4 = cl.BackgroundMixDataset(infos, lambda r: dict(r, imgs=torch.zeros(2, 3, 4, 4), randAug=True),
+                                  bg_dir=str(bg), extract_bg_if_not_found=False, with_randAug=True)
+    r = ds4.prepare_train_frames(0)
+    assert r["bg_idx"] == -1 and torch.equal(r["imgs"], torch.zeros(2, 3, 4, 4))
+    random.seed(0)
+    ds5 = cl.BackgroundMixDataset(infos, lambda r: dict(r, imgs=torch.zeros(2, 3, 4, 4)), bg_dir=str(bg),
+                                  extract_bg_if_not_found=False, prob=0.0)
+    assert ds5.prepare_train_frames(1)["bg_idx"] == -1
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bgdebias_b200.pool import BackgroundPool
+    n = 3 if rank == 0 else 1                                   # ragged shards
+    names = [f"r{rank}_v{i}" for i in range(n)]
+    bgs = torch.full((n, 4, 5, 3), rank + 1, dtype=torch.uint8) + torch.arange(n, dtype=torch.uint8).view(n, 1, 1, 1)
+    all_names, all_bgs = BackgroundPool.all_gather(names, bgs)
+    q.put((rank, all_names, all_bgs.numpy()))
+    dist.destroy_process_group()
+
+
+def test_pool_all_gather_two_ranks():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp_names = ["r0_v0", "r0_v1", "r0_v2", "r1_v0"]
+    for rank, names, bgs in res:
+        assert names == exp_names
+        assert bgs.shape == (4, 4, 5, 3)
+        assert [int(bgs[i, 0, 0, 0]) for i in range(4)] == [1, 2, 3, 2]
