@@ -175,8 +175,13 @@ struct Stager {
     cudaEvent_t done[kSlots] = {nullptr, nullptr};
     int device = -1;
 
-    int ensure(int dev, size_t in_bytes, size_t out_bytes)
+    size_t h_in_cap = 0, h_out_cap = 0;
+
+    // device slabs of in_bytes / out_bytes; pinned mirrors only as large as asked (0 = caller's memory is pinned)
+    int ensure(int dev, size_t in_bytes, size_t out_bytes, size_t h_in_bytes = (size_t)-1, size_t h_out_bytes = (size_t)-1)
     {
+        if (h_in_bytes == (size_t)-1) h_in_bytes = in_bytes;
+        if (h_out_bytes == (size_t)-1) h_out_bytes = out_bytes;
         BGD_CUDA_TRY(cudaSetDevice(dev));
         if (dev != device) {
             release_all();
@@ -187,30 +192,28 @@ struct Stager {
             }
         }
         if (in_bytes > in_cap) {
-            for (int s = 0; s < kSlots; ++s) {
-                if (h_in[s]) cudaFreeHost(h_in[s]);
-                if (d_in[s]) cudaFree(d_in[s]);
-                h_in[s] = d_in[s] = nullptr;
-            }
+            for (int s = 0; s < kSlots; ++s) { if (d_in[s]) cudaFree(d_in[s]); d_in[s] = nullptr; }
             in_cap = 0;
-            for (int s = 0; s < kSlots; ++s) {
-                BGD_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_in[s]), in_bytes));
-                BGD_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_in[s]), in_bytes));
-            }
+            for (int s = 0; s < kSlots; ++s) BGD_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_in[s]), in_bytes));
             in_cap = in_bytes;
         }
+        if (h_in_bytes > h_in_cap) {
+            for (int s = 0; s < kSlots; ++s) { if (h_in[s]) cudaFreeHost(h_in[s]); h_in[s] = nullptr; }
+            h_in_cap = 0;
+            for (int s = 0; s < kSlots; ++s) BGD_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_in[s]), h_in_bytes));
+            h_in_cap = h_in_bytes;
+        }
         if (out_bytes > out_cap) {
-            for (int s = 0; s < kSlots; ++s) {
-                if (h_out[s]) cudaFreeHost(h_out[s]);
-                if (d_out[s]) cudaFree(d_out[s]);
-                h_out[s] = d_out[s] = nullptr;
-            }
+            for (int s = 0; s < kSlots; ++s) { if (d_out[s]) cudaFree(d_out[s]); d_out[s] = nullptr; }
             out_cap = 0;
-            for (int s = 0; s < kSlots; ++s) {
-                BGD_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_out[s]), out_bytes));
-                BGD_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_out[s]), out_bytes));
-            }
+            for (int s = 0; s < kSlots; ++s) BGD_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_out[s]), out_bytes));
             out_cap = out_bytes;
+        }
+        if (h_out_bytes > h_out_cap) {
+            for (int s = 0; s < kSlots; ++s) { if (h_out[s]) cudaFreeHost(h_out[s]); h_out[s] = nullptr; }
+            h_out_cap = 0;
+            for (int s = 0; s < kSlots; ++s) BGD_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h_out[s]), h_out_bytes));
+            h_out_cap = h_out_bytes;
         }
         return BGD_OK;
     }
@@ -227,7 +230,7 @@ struct Stager {
             stream[s] = nullptr;
             done[s] = nullptr;
         }
-        in_cap = out_cap = 0;
+        in_cap = out_cap = h_in_cap = h_out_cap = 0;
     }
 };
 
@@ -235,6 +238,17 @@ static Stager &thread_stager()
 {
     static thread_local Stager st;
     return st;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
 }
 
 static size_t staging_slab_bytes()
@@ -277,8 +291,13 @@ static int median_host_pipeline(const uint8_t *const *frame_ptrs, const uint8_t 
     }
     int64_t max_videos = 0;
     for (auto &c : chunks) max_videos = std::max(max_videos, c.second - c.first);
+    // page-locked caller buffers are copied from / into directly; pageable ones go through pinned mirrors
+    const bool in_pinned = frames && is_pinned_host(frames);
+    const bool out_pinned = is_pinned_host(h_out);
     Stager &st = thread_stager();
-    if (int rc = st.ensure(device, slab, (size_t)max_videos * N)) return rc;
+    if (int rc = st.ensure(device, slab, (size_t)max_videos * N, in_pinned ? 0 : slab,
+                           out_pinned ? 64 : (size_t)max_videos * N))
+        return rc;
 
     std::vector<int64_t> local;
     int pending_slot_chunk[Stager::kSlots] = {-1, -1};
@@ -286,7 +305,7 @@ static int median_host_pipeline(const uint8_t *const *frame_ptrs, const uint8_t 
         if (pending_slot_chunk[slot] < 0) return BGD_OK;
         BGD_CUDA_TRY(cudaEventSynchronize(st.done[slot]));
         const auto &c = chunks[pending_slot_chunk[slot]];
-        std::memcpy(h_out + c.first * N, st.h_out[slot], (size_t)(c.second - c.first) * N);
+        if (!out_pinned) std::memcpy(h_out + c.first * N, st.h_out[slot], (size_t)(c.second - c.first) * N);
         pending_slot_chunk[slot] = -1;
         return BGD_OK;
     };
@@ -295,18 +314,25 @@ static int median_host_pipeline(const uint8_t *const *frame_ptrs, const uint8_t 
         if (int rc = drain(slot)) return rc;
         const int64_t v0 = chunks[ci].first, v1 = chunks[ci].second;
         const int64_t r0 = h_offsets[v0], r1 = h_offsets[v1];
-        // pack the chunk into the pinned slab (gathers separately allocated frames)
-        if (frame_ptrs) {
-            for (int64_t r = r0; r < r1; ++r) std::memcpy(st.h_in[slot] + (size_t)(r - r0) * N, frame_ptrs[r], (size_t)N);
+        const uint8_t *src = nullptr;
+        if (in_pinned) {
+            src = frames + (size_t)r0 * N;
         } else {
-            std::memcpy(st.h_in[slot], frames + (size_t)r0 * N, (size_t)(r1 - r0) * N);
+            // pack the chunk into the pinned slab (gathers separately allocated frames)
+            if (frame_ptrs) {
+                for (int64_t r = r0; r < r1; ++r) std::memcpy(st.h_in[slot] + (size_t)(r - r0) * N, frame_ptrs[r], (size_t)N);
+            } else {
+                std::memcpy(st.h_in[slot], frames + (size_t)r0 * N, (size_t)(r1 - r0) * N);
+            }
+            src = st.h_in[slot];
         }
         cudaStream_t s = st.stream[slot];
-        BGD_CUDA_TRY(cudaMemcpyAsync(st.d_in[slot], st.h_in[slot], (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, s));
+        BGD_CUDA_TRY(cudaMemcpyAsync(st.d_in[slot], src, (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, s));
         local.resize((size_t)(v1 - v0 + 1));
         for (int64_t v = v0; v <= v1; ++v) local[(size_t)(v - v0)] = h_offsets[v] - r0;
         if (int rc = median_varlen_dispatch(st.d_in[slot], local.data(), v1 - v0, N, st.d_out[slot], s)) return rc;
-        BGD_CUDA_TRY(cudaMemcpyAsync(st.h_out[slot], st.d_out[slot], (size_t)(v1 - v0) * N, cudaMemcpyDeviceToHost, s));
+        uint8_t *dst = out_pinned ? h_out + (size_t)v0 * N : st.h_out[slot];
+        BGD_CUDA_TRY(cudaMemcpyAsync(dst, st.d_out[slot], (size_t)(v1 - v0) * N, cudaMemcpyDeviceToHost, s));
         BGD_CUDA_TRY(cudaEventRecord(st.done[slot], s));
         pending_slot_chunk[slot] = (int)ci;
     }

@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- background-extraction frames/s (and BG-mix clips/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): the UCF101-shaped set -- 13,320 videos, T ~ U[120,240] frames
+of 240x320x3 uint8 -- sharded over 8 GPUs: 1,665 videos (~69 GB) per GPU, one process per GPU, no
+collective on the data path (weak scaling: every rank always owns one 1,665-video shard).  A "step"
+is one pass of the temporal-median extraction over the rank's resident shard.
+
+One JSON line on stdout (rank 0):
+  value      frames/s over all ranks, inputs resident in HBM (CUDA events, max over ranks)
+  e2e        frames/s through the C-ABI host call (pinned host frames -> H2D -> kernel -> D2H)
+  roofline   algorithmic bytes of a step / event time of a step vs the measured HBM peak
+  cpu_baseline  the reference's np.median path on this box's cores, bounded sample
+  bgmix      BASELINE.json configs[4]: fused blend, 64 x 8 x 224 x 224 clips per step
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W = 240, 320
+N_BYTES = H * W * 3
+VIDEOS_TOTAL, SHARDS = 13320, 8
+VIDEOS_PER_GPU = VIDEOS_TOTAL // SHARDS            # 1665
+T_LO, T_HI = 120, 241
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own computation, np.median(frames, axis=0).astype(uint8)
+# (cil_tools/extract_background.py:73), one video per call, fanned out over processes like
+# extract_background.py:154-162.  Lives in oracle/ (test infrastructure); only timed here.
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n_videos = args
+    import numpy as np
+    from oracle import median_oracle as mo
+    rng = np.random.default_rng(seed)
+    vids = []
+    for _ in range(n_videos):
+        T = int(rng.integers(T_LO, T_HI))
+        vids.append([rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(T)])   # the `frames` list
+    t0 = time.perf_counter()
+    for frames in vids:
+        mo.temporal_median_np(frames)
+    return time.perf_counter() - t0, sum(len(v) for v in vids)
+
+
+def cpu_reference_fps(n_procs: int, videos_per_proc: int, seed: int = 0):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(n_procs) as pool:
+        res = pool.map(_cpu_worker, [(seed * 1000 + i, videos_per_proc) for i in range(n_procs)])
+    t = max(r[0] for r in res)
+    frames = sum(r[1] for r in res)
+    return frames / t, frames, t
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:           # pragma: no cover
+            self.nv = None
+            log("NVML unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    procs = max(1, min(cores, 64))
+    vpp = 1
+    for _ in range(args.warmup):
+        cpu_reference_fps(procs, vpp, seed=99)
+    t_all, f_all = 0.0, 0
+    for s in range(args.steps):
+        fps, frames, t = cpu_reference_fps(procs, vpp, seed=s)
+        t_all += t
+        f_all += frames
+    value = f_all / t_all
+    sample = f"{procs} videos per step (one per process), T~U[120,240], 240x320x3, np.median only (no decode)"
+    print(json.dumps({
+        "impl": "reference", "metric": "bg_extraction_frames_per_sec", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "UCF101-shaped shard of configs[1] (T~U[120,240], 240x320x3 uint8); bounded sample per step",
+                   "videos_per_step": procs},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bgdebias_b200.ops as ops
+    from bgdebias_b200 import _cabi
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bgdebias_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+
+    # ---- the rank's shard, resident in HBM --------------------------------------------------
+    V = int(os.environ.get("BGD_BENCH_VIDEOS", VIDEOS_PER_GPU))
+    rng = np.random.default_rng(1 + rank)
+    Ts = rng.integers(T_LO, T_HI, V)
+    free, _total = torch.cuda.mem_get_info(dev)
+    while int(Ts.sum()) * N_BYTES + (4 << 30) > free and V > 16:          # another tenant on the GPU: shrink, say so
+        V //= 2
+        Ts = Ts[:V]
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64))
+    rows = int(offs[-1])
+    frames = torch.empty((rows, N_BYTES), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    chunk = max(1, (1 << 30) // N_BYTES)
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        frames[r0:r1] = torch.randint(0, 256, (r1 - r0, N_BYTES), dtype=torch.uint8, device=dev, generator=g)
+    torch.cuda.synchronize()
+    step_bytes = (rows + V) * N_BYTES                      # every frame byte read once + one frame written per video
+
+    def step():
+        return torch.ops.bgdebias.temporal_median_varlen(frames, offs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    launches0 = _cabi.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        nvml_index = torch.cuda._get_nvml_device_index(local_rank)
+    except Exception:
+        nvml_index = local_rank
+    with ClockSampler(nvml_index) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _cabi.kernel_launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(rows)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, frames_total = float(t.item()), float(tot.item())
+    value = frames_total * args.steps / (ms_max * 1e-3)
+    ms_per_step = ms_max / args.steps
+
+    # spot-check the timed path against the oracle (checker only; outside the timed region)
+    from oracle import c_oracle
+    v_chk = int(np.argmin(Ts))
+    sl = slice(int(offs[v_chk]), int(offs[v_chk + 1]))
+    ok = bool(np.array_equal(out[v_chk].cpu().numpy(), c_oracle.temporal_median(frames[sl].cpu().numpy())))
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    Ve = int(os.environ.get("BGD_BENCH_E2E_VIDEOS", 48))
+    Te = Ts[:Ve]
+    offs_e = np.concatenate([[0], np.cumsum(Te)]).astype(np.int64)
+    rows_e = int(offs_e[-1])
+    h_frames = torch.empty((rows_e, N_BYTES), dtype=torch.uint8, pin_memory=True)
+    h_frames.copy_(frames[:rows_e])
+    h_out = torch.empty((Ve, N_BYTES), dtype=torch.uint8, pin_memory=True)
+    L = _cabi.lib()
+    optr = offs_e.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+    def e2e_step():
+        _cabi.check(L.bgd_temporal_median_varlen_u8_host(h_frames.data_ptr(), optr, Ve, N_BYTES, h_out.data_ptr(),
+                                                         local_rank))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    k_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * rows_e * k_e2e / float(te.item())
+    e2e_ok = bool(torch.equal(h_out.to(dev), out[:Ve]))
+
+    # ---- BG-mix (configs[4]): 64 clips x 8 x 224 x 224 per step --------------------------------
+    bgmix = None
+    try:
+        B, Tm, Hm, Wm, P = 64, 8, 224, 224, 1024
+        gm = torch.Generator(device=dev).manual_seed(4)
+        fg = torch.randint(0, 256, (B, Tm, Hm, Wm, 3), dtype=torch.uint8, device=dev, generator=gm)
+        pool = torch.rand((P, 3, 256, 341), device=dev, generator=gm) * 255.0
+        torch.manual_seed(0)
+        idx = torch.randint(0, P, (B,)).int().to(dev)
+        top = torch.randint(0, 33, (B,)).int().to(dev)
+        left = torch.randint(0, 118, (B,)).int().to(dev)
+        app = torch.ones(B, dtype=torch.uint8, device=dev)
+        mean, std = torch.tensor([123.675, 116.28, 103.53]), torch.tensor([58.395, 57.12, 57.375])
+        lut = ops.make_fg_lut(mean.tolist(), std.tolist(), dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > L2 (126 MB)
+        mix = lambda: torch.ops.bgdebias.bgmix_blend(fg, pool, idx, top, left, app, lut, mean, std, 0.5, "NTCHW")
+        for _ in range(3):
+            mix()
+        times = []
+        for _ in range(max(5, args.steps)):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); o = mix(); b.record(); torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        mix_ms = sorted(times)[len(times) // 2]
+        mix_bytes = B * (Tm * Hm * Wm * 3 * 5 + Hm * Wm * 3 * 4)
+        # end to end: pinned uint8 clips + draws in host memory -> training tensor on device + checksum back
+        h_fg = torch.empty(fg.shape, dtype=torch.uint8, pin_memory=True); h_fg.copy_(fg)
+        hi, ht, hl, ha = (x.cpu().numpy().copy() for x in (idx, top, left, app))
+        d_out = torch.empty((B, Tm, 3, Hm, Wm), dtype=torch.float32, device=dev)
+        chk = ctypes.c_double()
+        call = lambda: _cabi.check(L.bgd_bgmix_blend_f32_host(
+            h_fg.data_ptr(), B, Tm, Hm, Wm, pool.data_ptr(), P, 256, 341, hi.ctypes.data, ht.ctypes.data, hl.ctypes.data,
+            ha.ctypes.data, lut.data_ptr(), _cabi.f32x3(mean.tolist()), _cabi.f32x3(std.tolist()), 0.5, 0,
+            d_out.data_ptr(), ctypes.byref(chk), local_rank))
+        call(); call()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            call()
+        mix_e2e = 5 * B / (time.perf_counter() - t0)
+        peak, _ = measured_peak_gbs()
+        bgmix = {"metric": "bgmix_clips_per_sec", "value": world * B / (mix_ms * 1e-3), "unit": "clips/s",
+                 "ms_per_step": mix_ms, "config": {"workload": "configs[4]: fg u8 [64,8,224,224,3], fp32 pool 1024x3x256x341, alpha 0.5, all samples mixed, out fp32 [64,8,3,224,224]", "l2": "256 MB flush write between iterations"},
+                 "roofline": {"bound": "hbm", "achieved": mix_bytes / (mix_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": mix_bytes / (mix_ms * 1e-3) / 1e9 / peak, "traffic": None},
+                 "e2e": {"value": world * mix_e2e, "unit": "clips/s", "h2d_bytes_per_step": int(h_fg.numel() + B * 13),
+                         "d2h_bytes_per_step": 8},
+                 "parity_spotcheck": bool(torch.equal(d_out, o))}
+        del fg, pool, flush, d_out, h_fg
+    except Exception as e:           # the headline metric stands even if the secondary bench cannot run
+        bgmix = {"error": repr(e)}
+
+    if rank == 0:
+        cb = None
+        try:
+            procs = max(1, min(host_cores(), 32))
+            fps, nfr, tt = cpu_reference_fps(procs, 2, seed=7)
+            cb = {"value": fps, "unit": "frames/s", "cores": procs, "kind": "port",
+                  "sample": f"{2 * procs} videos of the same workload ({nfr} frames, {tt:.1f} s), np.median(frames,0).astype(uint8) per video, one process per core"}
+        except Exception as e:
+            cb = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(e)}
+        peak, peak_src = measured_peak_gbs()
+        achieved = step_bytes / (ms_per_step * 1e-3) / 1e9          # this rank's step bytes / max step time
+        traffic = None
+        tf = ROOT / "profiles" / "r1_traffic.json"
+        if tf.exists():
+            try:
+                ratio = json.loads(tf.read_text())["dram_bytes_per_algorithmic_byte"]
+                traffic = ratio * step_bytes
+            except Exception:
+                traffic = None
+        print(json.dumps({
+            "metric": "bg_extraction_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: UCF101-shaped set, one 1/8 shard per GPU", "videos_per_gpu": V,
+                       "frames_per_gpu": rows, "frame_shape": [H, W, 3], "T": "U[120,240]", "resident_gb": rows * N_BYTES / 1e9,
+                       "l2": "inputs (>60 GB per GPU) exceed L2; no flush needed", "kernel": "median_colplane (AUTO)",
+                       "parallelism": f"shard x{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": rows_e * N_BYTES,
+                    "d2h_bytes_per_step": Ve * N_BYTES, "videos_per_step": Ve, "parity": e2e_ok},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": step_bytes,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "cpu_baseline": cb,
+            "clocks": clk.summary(),
+            "parity_spotcheck": ok,
+            "bgmix": bgmix,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
