@@ -468,17 +468,24 @@ int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t 
     BGD_CUDA_TRY(cudaSetDevice(device));
     const size_t fg_bytes = (size_t)B * T * H * W * 3;
     const size_t par_bytes = (size_t)B * 13 + 64;
+    const bool fg_pinned = is_pinned_host(h_fg);      // page-locked clips are copied straight from the caller's buffer
     Stager &st = thread_stager();
-    if (int rc = st.ensure(device, fg_bytes + par_bytes + 64, 64)) return rc;
+    if (int rc = st.ensure(device, fg_bytes + par_bytes + 64, 64, (fg_pinned ? 0 : fg_bytes) + par_bytes + 64, 64)) return rc;
     cudaStream_t s = st.stream[0];
     uint8_t *hp = st.h_in[0], *dp_ = st.d_in[0];
-    std::memcpy(hp, h_fg, fg_bytes);
-    size_t o = (fg_bytes + 15) & ~(size_t)15;
-    std::memcpy(hp + o, h_bg_idx, (size_t)B * 4);
-    std::memcpy(hp + o + (size_t)B * 4, h_top, (size_t)B * 4);
-    std::memcpy(hp + o + (size_t)B * 8, h_left, (size_t)B * 4);
-    std::memcpy(hp + o + (size_t)B * 12, h_apply, (size_t)B);
-    BGD_CUDA_TRY(cudaMemcpyAsync(dp_, hp, o + (size_t)B * 13, cudaMemcpyHostToDevice, s));
+    const size_t o = (fg_bytes + 15) & ~(size_t)15;     // device layout: clips | bg_idx | top | left | apply
+    uint8_t *hpar = fg_pinned ? hp : hp + o;
+    if (!fg_pinned) std::memcpy(hp, h_fg, fg_bytes);
+    std::memcpy(hpar, h_bg_idx, (size_t)B * 4);
+    std::memcpy(hpar + (size_t)B * 4, h_top, (size_t)B * 4);
+    std::memcpy(hpar + (size_t)B * 8, h_left, (size_t)B * 4);
+    std::memcpy(hpar + (size_t)B * 12, h_apply, (size_t)B);
+    if (fg_pinned) {
+        BGD_CUDA_TRY(cudaMemcpyAsync(dp_, h_fg, fg_bytes, cudaMemcpyHostToDevice, s));
+        BGD_CUDA_TRY(cudaMemcpyAsync(dp_ + o, hpar, (size_t)B * 13, cudaMemcpyHostToDevice, s));
+    } else {
+        BGD_CUDA_TRY(cudaMemcpyAsync(dp_, hp, o + (size_t)B * 13, cudaMemcpyHostToDevice, s));
+    }
     const int32_t *d_idx = reinterpret_cast<const int32_t *>(dp_ + o);
     if (int rc = launch_bgmix(dp_, nullptr, B, T, H, W, d_bg_pool, false, P, Hb, Wb, d_idx, d_idx + B, d_idx + 2 * B,
                               dp_ + o + (size_t)B * 12, d_fg_lut, h_bg_mean, h_bg_std, alpha, layout, d_out, s))
