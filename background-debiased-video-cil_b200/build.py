@@ -16,8 +16,9 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-OBJ = CSRC / "_obj"
-LIB = PKG / "libbgdebias_b200.so"
+OBJ = CSRC / ("_obj" + ("_" + os.environ["BGD_BUILD_OUT"].replace(".", "_") if os.environ.get("BGD_BUILD_OUT") else ""))
+LIB = PKG / os.environ.get("BGD_BUILD_OUT", "libbgdebias_b200.so")
+EXTRA_DEFINES = [d for d in os.environ.get("BGD_BUILD_DEFINES", "").split() if d]
 SOURCES = ["api.cu", "median_swar.cu", "median_bitsliced.cu", "median_colplane.cu", "median_colplane_c1.cu",
            "median_colplane_c2.cu", "median_colplane_c4.cu", "bgmix.cu"]
 
@@ -42,7 +43,7 @@ def _stamp() -> str:
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "bgdebias.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_DEFINES).encode())
     return h.hexdigest()
 
 
@@ -56,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: str) -> None:
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(OBJ / (src + ".o"))]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_DEFINES, *extra, "-c", str(CSRC / src), "-o", str(OBJ / (src + ".o"))]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

@@ -103,6 +103,19 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t mask
     return d;
 }
 
+// x >> S.  LOP3/SHF share one half-rate pipe (64 lanes/clk/SM) and the kernel is bound by it.  The
+// FMA-pipe alternative, a multiply-high by 2^(32-S) (IMAD.HI), measured 32 lanes/clk/SM on B200
+// (profiles/r1_microbench_instruction_throughput.txt) and made the kernel ~1% slower, so SHF stays.
+template <int S>
+__device__ __forceinline__ uint32_t shr(uint32_t x)
+{
+#ifdef BGD_SHR_ON_FMA
+    return __umulhi(x, 1u << (32 - S));
+#else
+    return x >> S;
+#endif
+}
+
 // ---- bit-plane arithmetic -----------------------------------------------------------------
 __device__ __forceinline__ void full_add(uint32_t &acc, uint32_t x, uint32_t y, uint32_t &carry)
 {
@@ -115,17 +128,27 @@ __device__ __forceinline__ void half_add(uint32_t &acc, uint32_t x, uint32_t &ca
     carry = acc & x;
     acc ^= x;
 }
-// Adds N words of weight 2^L into the bit-sliced counter c[0..NPL) (carries past NPL-1 are zero by sizing).
+// Vertical count of N one-bit words: planes[L..] receive the binary digits of the per-bit-position
+// sum.  Each weight is reduced to one word with 3:2 compressors ((N-1)/2 full adders, at most one
+// half adder); the carries form the next weight's inputs.
 template <int NPL, int L, int N>
-__device__ __forceinline__ void csa_add(uint32_t (&c)[NPL], const uint32_t (&x)[N])
+__device__ __forceinline__ void csa_count(uint32_t (&planes)[NPL], const uint32_t (&x)[N])
 {
-    if constexpr (L < NPL && N > 0) {
-        constexpr int NC = (N + 1) / 2;
-        uint32_t carry[NC];
+    static_assert(N >= 1, "csa_count needs at least one word");
+    if constexpr (L < NPL) {
+        constexpr int NFA = (N - 1) / 2, NHA = (N - 1) % 2, NC = NFA + NHA;
+        uint32_t acc = x[0];
+        uint32_t carry[NC > 0 ? NC : 1];
 #pragma unroll
-        for (int i = 0; i + 1 < N; i += 2) full_add(c[L], x[i], x[i + 1], carry[i / 2]);
-        if constexpr (N & 1) half_add(c[L], x[N - 1], carry[NC - 1]);
-        csa_add<NPL, L + 1, NC>(c, carry);
+        for (int i = 0; i < NFA; ++i) full_add(acc, x[1 + 2 * i], x[2 + 2 * i], carry[i]);
+        if constexpr (NHA) half_add(acc, x[N - 1], carry[NFA]);
+        planes[L] = acc;
+        if constexpr (NC > 0) {
+            csa_count<NPL, L + 1, (NC > 0 ? NC : 1)>(planes, carry);
+        } else {
+#pragma unroll
+            for (int l = L + 1; l < NPL; ++l) planes[l] = 0u;
+        }
     }
 }
 // 8x8 bit-matrix transpose across 8 registers: w[m] byte y bit b  ->  w[b] byte y bit m.
@@ -135,20 +158,20 @@ __device__ __forceinline__ void bit_transpose8(uint32_t (&w)[8])
     for (int k = 0; k < 4; ++k) {
         const uint32_t t = w[k], u = w[k + 4];
         w[k] = bitsel(t, u << 4, 0x0F0F0F0Fu);
-        w[k + 4] = bitsel(t >> 4, u, 0x0F0F0F0Fu);
+        w[k + 4] = bitsel(shr<4>(t), u, 0x0F0F0F0Fu);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int k = (q & 1) | ((q & 2) << 1);          // 0, 1, 4, 5
         const uint32_t t = w[k], u = w[k + 2];
         w[k] = bitsel(t, u << 2, 0x33333333u);
-        w[k + 2] = bitsel(t >> 2, u, 0x33333333u);
+        w[k + 2] = bitsel(shr<2>(t), u, 0x33333333u);
     }
 #pragma unroll
     for (int k = 0; k < 8; k += 2) {
         const uint32_t t = w[k], u = w[k + 1];
         w[k] = bitsel(t, u << 1, 0x55555555u);
-        w[k + 1] = bitsel(t >> 1, u, 0x55555555u);
+        w[k + 1] = bitsel(shr<1>(t), u, 0x55555555u);
     }
 }
 
@@ -281,23 +304,31 @@ __global__ void __launch_bounds__(kMaxThreads) median_colplane_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < NW; ++k) z[k] = alive[k] & P[k][b];
             uint32_t cs[NPC];
-#pragma unroll
-            for (int q = 0; q < NPC; ++q) cs[q] = 0u;
-            csa_add<NPC, 0, NW>(cs, z);
+            csa_count<NPC, 0, NW>(cs, z);
             uint32_t any0 = 0u;                          // rows of the second rank's set whose bit is 0
             if (EVEN) {
 #pragma unroll
                 for (int k = 0; k < NW; ++k) any0 |= alive2[k] & ~P[k][b];
             }
             uint32_t keep1 = 0u, keep2 = 0u;             // column masks where the chosen bit is 1
+            int ones_all = 0;                            // over all C columns (C == 2: second column = all - first)
+            if constexpr (C == 2) {
+#pragma unroll
+                for (int q = 0; q < NPC; ++q) ones_all += __popc(cs[q]) << q;
+            }
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                constexpr uint32_t kAll = 0xFFFFFFFFu;
                 const uint32_t M = col_mask<C>(c);
                 int ones = 0;
+                if (C == 2 && c == 1) {
+                    ones = ones_all;                     // ones_all has had column 0 subtracted below
+                } else {
 #pragma unroll
-                for (int q = 0; q < NPC; ++q) ones += __popc(C == 1 ? cs[q] : (cs[q] & M)) << q;
+                    for (int q = 0; q < NPC; ++q) ones += __popc(C == 1 ? cs[q] : (cs[q] & M)) << q;
+                    if (C == 2) ones_all -= ones;
+                }
                 const int zeros = cnt[c] - ones;
+#ifndef BGD_RANK_ARITH
                 const bool take0 = rank[c] < zeros;
                 bool take0_2 = take0;
                 if (EVEN) {
@@ -307,11 +338,30 @@ __global__ void __launch_bounds__(kMaxThreads) median_colplane_kernel(const __gr
                 cnt[c] = take0 ? zeros : ones;
                 rank[c] = take0 ? rank[c] : rank[c] - zeros;
                 lo[c] |= take0 ? 0 : (1 << b);
-                keep1 |= take0 ? 0u : (C == 1 ? kAll : M);
+                keep1 |= take0 ? 0u : M;
                 if (EVEN) {
                     hi[c] |= take0_2 ? 0 : (1 << b);
-                    keep2 |= take0_2 ? 0u : (C == 1 ? kAll : M);
+                    keep2 |= take0_2 ? 0u : M;
                 }
+#else
+                // the same decisions as arithmetic on 0/1 integers (multiplies on the FMA pipe); measured
+                // 3-8% slower than the select form above on B200, kept for experiments only
+                const int d = rank[c] - zeros;                       // < 0  <=>  the bit is 0
+                const uint32_t one = 1u - ((uint32_t)d >> 31);       // chosen bit of the lower middle
+                cnt[c] = zeros + (int)one * (ones - zeros);
+                rank[c] = rank[c] - (int)one * zeros;
+                lo[c] += (int)(one << b);
+                keep1 += one * M;
+                if (EVEN) {
+                    const uint32_t shared = 1u - ((uint32_t)(d + 1) >> 31);               // rank + 1 >= zeros
+                    const uint32_t alone = ((any0 & M) == 0u) ? 1u : 0u;                  // min of its own set
+                    const uint32_t dv = diverged[c] ? 1u : 0u;
+                    const uint32_t two = dv * alone + (1u - dv) * shared;
+                    diverged[c] = diverged[c] || (two != one);
+                    hi[c] += (int)(two << b);
+                    keep2 += two * M;
+                }
+#endif
             }
 #pragma unroll
             for (int k = 0; k < NW; ++k) alive[k] &= ~(P[k][b] ^ keep1);

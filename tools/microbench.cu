@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #define CHAINS 8
@@ -34,6 +35,15 @@ __device__ __forceinline__ void step(uint32_t (&a)[CHAINS], uint32_t b, uint32_t
             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
             asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
         }
+        if (OP == 13) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(0x10000000u));
+        if (OP == 14) {   // transpose pair with both shifts on the fma pipe: 2 lop3 + mul.lo + mul.hi
+            uint32_t t;
+            asm volatile("mul.lo.u32 %0, %1, 16;" : "=r"(t) : "r"(a[i]));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE4;" : "+r"(a[i]) : "r"(t), "r"(b));
+            asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(a[i]), "r"(0x10000000u));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xD8;" : "+r"(a[i]) : "r"(t), "r"(c));
+        }
+        if (OP == 16) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
         if (OP == 12) {   // mix: lop3 + vabsdiff4
             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
             asm volatile("vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
@@ -154,7 +164,11 @@ int main()
     run<10>("transpose pair (4 ops)", 4, sms, d_out, d_cyc);
     run<11>("lop3+imad", 2, sms, d_out, d_cyc);
     run<12>("lop3+vabsdiff4", 2, sms, d_out, d_cyc);
+    run<13>("mul.hi (imad.hi)", 1, sms, d_out, d_cyc);
+    run<14>("transpose pair, shifts on fma", 4, sms, d_out, d_cyc);
+    run<16>("mad.hi", 1, sms, d_out, d_cyc);
 
+    if (getenv("MB_NO_BW")) return 0;
     // bandwidth
     const size_t bytes = (size_t)8 << 30;
     uint8_t *d_src; cudaMalloc(&d_src, bytes); cudaMemset(d_src, 1, bytes);

@@ -29,11 +29,14 @@ for case in cases:
     for var in [int(v) for v in os.environ.get("VARIANTS", "3").split(",")]:
         if var == 2: continue
         _cabi.set_median_variant(var)
-        for thr in [int(v) for v in os.environ.get("COLTHR", "128,256").split(",")]:
+        for thr, tc2, tc4 in itertools.product([int(v) for v in os.environ.get("COLTHR", "128,256").split(",")],
+                                               [int(v) for v in os.environ.get("TC2", "240").split(",")],
+                                               [int(v) for v in os.environ.get("TC4", "96").split(",")]):
             os.environ["BGD_COL_THREADS_C2"] = str(thr); os.environ["BGD_COL_THREADS_C4"] = str(thr)
+            os.environ["BGD_COL_T_C2"] = str(tc2); os.environ["BGD_COL_T_C4"] = str(tc4)
             try:
                 ms = run(fr, offs)
-                print(f"T={case:>5s} variant={var} col_threads={thr}: {ms:7.3f} ms {by/ms/1e6:7.1f} GB/s {rows/ms/1e3:6.2f} Mframes/s", flush=True)
+                print(f"T={case:>5s} variant={var} col_threads={thr} t_c2={tc2} t_c4={tc4}: {ms:7.3f} ms {by/ms/1e6:7.1f} GB/s {rows/ms/1e3:6.2f} Mframes/s", flush=True)
             except Exception as e:
                 print(f"T={case} variant={var} thr={thr}: ERROR {e}", flush=True)
     _cabi.set_median_variant(2)
