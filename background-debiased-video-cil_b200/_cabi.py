@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libbgdebias_b200.so"
 
 BGD_OK, BGD_ERR_INVALID, BGD_ERR_CUDA, BGD_ERR_UNSUPPORTED, BGD_ERR_NO_DEVICE = range(5)
 LAYOUT_NTCHW, LAYOUT_NCTHW = 0, 1
-MEDIAN_AUTO, MEDIAN_SWAR, MEDIAN_BITSLICED, MEDIAN_COLPLANE = 0, 1, 2, 3
+MEDIAN_AUTO, MEDIAN_SWAR, MEDIAN_BITSLICED, MEDIAN_COLPLANE, MEDIAN_LDSM = 0, 1, 2, 3, 4
 LAYOUTS = {"NTCHW": LAYOUT_NTCHW, "NCTHW": LAYOUT_NCTHW}
 
 _c = ctypes

@@ -131,12 +131,13 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
     const bool aligned = reinterpret_cast<uintptr_t>(d_frames) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
     const bool can_col = aligned && median_colplane_supports(T_max, N);
     const bool can_bit = aligned && median_bitsliced_supports(T_max, N);
-    if ((variant == BGD_MEDIAN_COLPLANE && !can_col) || (variant == BGD_MEDIAN_BITSLICED && !can_bit))
+    if (((variant == BGD_MEDIAN_COLPLANE || variant == BGD_MEDIAN_LDSM) && !can_col) || (variant == BGD_MEDIAN_BITSLICED && !can_bit))
         return fail(BGD_ERR_UNSUPPORTED,
                     "median: the TMA variants need N %% 16 == 0, 16-byte aligned buffers and at most ~500 frames per video (T=%lld N=%lld)",
                     (long long)T_max, (long long)N);
-    if (variant == BGD_MEDIAN_COLPLANE || (variant == BGD_MEDIAN_AUTO && can_col))
-        return median_colplane_varlen(d_frames, h_offsets, V, N, d_out, stream);
+    // AUTO / LDSM: videos of up to 256 frames take the transposing-load kernel, longer ones the column-plane kernel
+    if (variant == BGD_MEDIAN_COLPLANE || variant == BGD_MEDIAN_LDSM || (variant == BGD_MEDIAN_AUTO && can_col))
+        return median_colplane_varlen(d_frames, h_offsets, V, N, d_out, variant != BGD_MEDIAN_COLPLANE, stream);
     if (variant == BGD_MEDIAN_BITSLICED || (variant == BGD_MEDIAN_AUTO && can_bit))
         return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
 
@@ -369,7 +370,7 @@ int64_t bgd_kernel_launch_count(void) { return g_launches.load(); }
 
 int bgd_median_set_variant(int variant)
 {
-    if (variant < BGD_MEDIAN_AUTO || variant > BGD_MEDIAN_COLPLANE)
+    if (variant < BGD_MEDIAN_AUTO || variant > BGD_MEDIAN_LDSM)
         return fail(BGD_ERR_INVALID, "unknown median variant %d", variant);
     g_variant.store(variant);
     return BGD_OK;

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "median_colplane.cuh"
+#include "median_ldsm.cuh"
 
 namespace bgd {
 
@@ -16,7 +17,7 @@ using colplane::kNumMaps;
 using colplane::kStripBytes;
 
 struct Key {
-    int C, NW, even;
+    int C, NW, even;   // C == 0: the transposing-load kernel (median_ldsm.cuh), 2 columns per lane, 32 rows per word
     bool operator<(const Key &o) const { return std::tie(C, NW, even) < std::tie(o.C, o.NW, o.even); }
 };
 
@@ -36,8 +37,12 @@ Tuning read_tuning()
     return t;
 }
 
-bool classify(int T, const Tuning &tn, Key *k)
+bool classify(int T, const Tuning &tn, bool use_ldsm, Key *k)
 {
+    if (use_ldsm && T <= 32 * ldsm::kMaxNW) {
+        *k = Key{0, (T + 31) / 32, (T & 1) == 0};
+        return true;
+    }
     int C = T <= tn.t_c4 ? 4 : (T <= tn.t_c2 ? 2 : 1);
     for (; C >= 1; C /= 2) {
         const int rpw = 32 / C;
@@ -76,11 +81,11 @@ bool median_colplane_supports(int64_t T_max, int64_t N)
     if (N <= 0 || N % 16 != 0 || N >= ((int64_t)1 << 31)) return false;
     if (T_max < 1 || T_max > 544) return false;
     Key k;
-    return classify((int)T_max, read_tuning(), &k);
+    return classify((int)T_max, read_tuning(), false, &k);
 }
 
 int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, uint8_t *d_out,
-                           cudaStream_t stream)
+                           bool use_ldsm, cudaStream_t stream)
 {
     if (V == 0 || N == 0) return BGD_OK;
     DeviceProps dp;
@@ -91,28 +96,41 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
 
     const int64_t row_lo = h_offsets[0], row_hi = h_offsets[V];
     if (row_hi - row_lo >= ((int64_t)1 << 31)) return fail(BGD_ERR_UNSUPPORTED, "median: more than 2^31 rows per call");
+    std::map<Key, std::vector<int64_t>> classes;
+    bool any_ldsm = false, any_col = false;
+    for (int64_t v = 0; v < V; ++v) {
+        Key k;
+        if (!classify((int)(h_offsets[v + 1] - h_offsets[v]), tn, use_ldsm, &k))
+            return fail(BGD_ERR_UNSUPPORTED, "median (column-plane): video %lld has too many frames", (long long)v);
+        classes[k].push_back(v);
+        (k.C == 0 ? any_ldsm : any_col) = true;
+    }
+
     CParams prm{};
+    ldsm::LParams lprm{};
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)(row_hi - row_lo)};
         const cuuint64_t gstride[1] = {(cuuint64_t)N};
         const cuuint32_t estride[2] = {1, 1};
         void *base = const_cast<uint8_t *>(d_frames) + row_lo * N;
         for (int k = 0; k < kNumMaps; ++k) {
-            const cuuint32_t box[2] = {(cuuint32_t)kStripBytes, (cuuint32_t)1 << k};
-            const CUresult r = encode(&prm.maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS)
-                return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a box of %d rows", (int)r, 1 << k);
+            if (any_col) {
+                const cuuint32_t box[2] = {(cuuint32_t)kStripBytes, (cuuint32_t)1 << k};
+                const CUresult r = encode(&prm.maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS)
+                    return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a box of %d rows", (int)r, 1 << k);
+            }
+            if (any_ldsm) {
+                const cuuint32_t box[2] = {(cuuint32_t)ldsm::kStripW, (cuuint32_t)1 << k};
+                const CUresult r = encode(&lprm.maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS)
+                    return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a swizzled box of %d rows", (int)r, 1 << k);
+            }
         }
-    }
-
-    std::map<Key, std::vector<int64_t>> classes;
-    for (int64_t v = 0; v < V; ++v) {
-        Key k;
-        if (!classify((int)(h_offsets[v + 1] - h_offsets[v]), tn, &k))
-            return fail(BGD_ERR_UNSUPPORTED, "median (column-plane): video %lld has too many frames", (long long)v);
-        classes[k].push_back(v);
     }
 
     // one table upload for all classes: row0[V] | out[V] | T[V], in class order
@@ -142,6 +160,23 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
     for (auto &kv : classes) {
         const Key key = kv.first;
         const int64_t nv = (int64_t)kv.second.size();
+        if (key.C == 0) {
+            lprm.out = d_out;
+            lprm.vid_row0 = d_row0 + pos;
+            lprm.vid_T = d_T + pos;
+            lprm.vid_out = d_outi + pos;
+            lprm.N = N;
+            lprm.tiles_per_video = (int32_t)((N + ldsm::kTileW - 1) / ldsm::kTileW);
+            lprm.num_tiles = nv * lprm.tiles_per_video;
+            lprm.rows_cap = key.NW * 32;
+            lprm.one = 1u;
+            // tile + mbarrier + slack to align the tile to the 1024-byte swizzle atom
+            const size_t smem = (size_t)lprm.rows_cap * ldsm::kTileW + 16 + 1024;
+            rc = ldsm::launch(key.NW, key.even != 0, lprm, dp.sm_count, smem, stream);
+            if (rc) break;
+            pos += nv;
+            continue;
+        }
         const int threads = key.C == 1 ? tn.threads_c1 : (key.C == 2 ? tn.threads_c2 : tn.threads_c4);
         const int tile_w = key.C * threads;
         const int rows_cap = key.NW * (32 / key.C);

@@ -1,0 +1,276 @@
+// Temporal median, transposing-load bit-plane select (BGD_MEDIAN_LDSM) -- the AUTO path for T <= 256.
+//
+// Replaces  np.median(frames, axis=0).astype(np.uint8)   (cil_tools/extract_background.py:73,
+// libs/loader/comix_loader.py:161); bit-exact:  out[n] = (s[(T-1)/2] + s[T/2]) >> 1.
+//
+// Same idea as median_colplane.cuh (one thread owns whole byte columns, so the 8-pass radix
+// select needs no communication), rebuilt around what the instruction-throughput probes
+// (profiles/r1_microbench2.txt) say about B200:
+//
+//  * LOP3/SHF/PRMT/SEL share one 64-lane/clk pipe and the column-plane kernel saturates it;
+//    POPC has its own 16-lane/clk pipe and IMAD runs on the FMA pipe, both idle there.
+//  * ldmatrix.m16n16.trans.b8 (SASS LDSM.8.MT1616) hands a lane 4 consecutive *rows* of one byte
+//    column in one register -- the shared-memory read and the byte gather the column-plane kernel
+//    spends 0.5 LDS + 0.25 PRMT per byte on become 1/16 instruction per byte.
+//
+// So: a CTA tile is [T rows] x [256 bytes], staged as two 128-byte-wide strips by 2-D TMA tensor
+// copies (boxes of 128 B x 2^k rows, 128-byte swizzle, one mbarrier).  The swizzle (16-byte chunk
+// index ^= row % 8) is what makes the transposing loads bank-conflict free: 122.7 B/clk/SM
+// measured against 32 B/clk/SM for an unswizzled 256-byte pitch.  Two warps share a strip; lane
+// (g = lane / 4, q = lane % 4) owns byte columns 16 chunk(q) + g and + 8 of it for ALL T rows,
+// chunk(q) = {0,4,1,5}[q] for the even warp and {2,6,3,7}[q] for the odd one.  One ldmatrix.x2
+// gives it 8 rows of both; 8 registers (32 rows) of a column are bit-transposed in place (3 stages of masked
+// shifts) into 8 plane words: word b holds bit b of 32 rows.  A column of T rows is NW =
+// ceil(T / 32) such groups.  Per pass b = 7..0 and word:  z = alive & plane_b (LOP3), POPC(z)
+// accumulated by IMAD (neither on the LOP3 pipe), and alive &= plane_b ^ keep (LOP3).  The rank
+// bookkeeping is 4 bitwise operations per column and pass.
+//  * Even T: the second rank (T/2) shares the first's state until the pass in which they
+//    disagree; after that it is the minimum of its own alive set (an OR over the words instead of
+//    a count).
+//  * As soon as every lane has its columns in registers the CTA's next tile is requested, so the
+//    TMA copies land while the select runs on registers; several CTAs per SM overlap the rest.
+#pragma once
+
+#include "median_colplane.cuh"
+
+namespace bgd {
+namespace ldsm {
+
+constexpr int kThreads = 128;
+constexpr int kTileW = 256;               // bytes per tile row
+constexpr int kStripW = 128;              // bytes per TMA strip (= the 128-byte swizzle span)
+constexpr int kMaxNW = 8;                 // T <= 256
+
+struct alignas(64) LParams {
+    CUtensorMap maps[colplane::kNumMaps];  // maps[k]: frames as [rows][N] uint8, box 128 bytes x 2^k rows, SWIZZLE_128B
+    uint8_t *out;
+    const int64_t *vid_row0;     // [n_videos] first row of each video (relative to the map's base)
+    const int32_t *vid_T;        // [n_videos]
+    const int64_t *vid_out;      // [n_videos] output slot
+    int64_t N;
+    int64_t num_tiles;
+    int32_t tiles_per_video;
+    int32_t rows_cap;            // smem rows per strip (= NW * 32)
+    uint32_t one;                // 1, opaque to the compiler: keeps count accumulation on IMAD
+};
+
+int launch(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);
+int launch_lo(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NW 1..4
+int launch_mid(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);  // NW 5..6
+int launch_hi(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NW 7..8
+
+#ifdef __CUDACC__
+using colplane::bit_transpose8;
+using colplane::fence_mbar_init;
+using colplane::fence_proxy_async;
+using colplane::mbar_arrive_expect_tx;
+using colplane::mbar_init;
+using colplane::mbar_wait;
+using colplane::policy_evict_first;
+using colplane::smem_u32;
+using colplane::tma_load_2d;
+
+// r0/r2: rows +0..3 / +4..7 of the lane's first column, r1/r3: the same rows of its second column
+__device__ __forceinline__ void ldsm_x2_trans_b8(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr)
+                 : "memory");
+}
+// acc + popc(x), the add issued as IMAD (FMA pipe): `one` is 1 at run time
+__device__ __forceinline__ int popc_acc(uint32_t x, int acc, uint32_t one)
+{
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(__popc(x)), "r"(one), "r"(acc));
+    return r;
+}
+// (a & mask) | (b & ~mask)
+__device__ __forceinline__ int isel(int a, int b, int mask)
+{
+    int d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(mask));
+    return d;
+}
+
+template <int NW> constexpr int min_blocks() { return NW <= 6 ? 4 : 3; }
+
+template <int NW, bool EVEN>
+__global__ void __launch_bounds__(kThreads, min_blocks<NW>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // the 128-byte swizzle pattern repeats every 1024 bytes of shared-memory address: align the tile to it
+    uint8_t *buf = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(buf + (size_t)prm.rows_cap * kTileW);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t one = prm.one;
+
+    const uint32_t strip_bytes = (uint32_t)prm.rows_cap * kStripW;
+    auto chunk_of = [&](int q) { return ((q & 1) << 2) + (q >> 1) + ((warp & 1) << 1); };
+    // ldmatrix address role: lane supplies row r8 = 4 * (lane / 16) + lane % 4 (mod 8) of the 16-byte
+    // chunk quarter (lane % 16) / 4 reads; chunk c of row r sits at 16 * (c ^ (r % 8))
+    const int r8 = ((lane >> 4) << 2) | (lane & 3);
+    const uint32_t ld_base = smem_u32(buf) + (uint32_t)(warp >> 1) * strip_bytes +
+                             (uint32_t)(r8 * kStripW + ((chunk_of((lane & 15) >> 2) ^ r8) << 4));
+    // data role: columns of the tile owned by this lane
+    const int colA = (warp >> 1) * kStripW + chunk_of(lane & 3) * 16 + (lane >> 2), colB = colA + 8;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint64_t policy = 0;
+    if (threadIdx.x == 0) policy = policy_evict_first();
+    auto issue_tile = [&](int64_t tile) {                // thread 0 only
+        const int64_t vid = tile / prm.tiles_per_video;
+        const int ct = (int)(tile - vid * prm.tiles_per_video);
+        const int T = prm.vid_T[vid];
+        const int64_t row0 = prm.vid_row0[vid];
+        mbar_arrive_expect_tx(bar, (uint32_t)T * (uint32_t)kTileW);
+#pragma unroll
+        for (int s = 0; s < kTileW / kStripW; ++s) {
+            const int col = ct * kTileW + s * kStripW;
+            uint8_t *dst = buf + (size_t)s * strip_bytes;
+            int r = 0;
+            if (T >= 256) {
+                tma_load_2d(dst, &prm.maps[8], col, (int)row0, bar, policy);
+                r = 256;
+            }
+#pragma unroll
+            for (int k = 7; k >= 0; --k)
+                if ((T - r) & (1 << k)) {
+                    tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[k], col, (int)(row0 + r), bar, policy);
+                    r += 1 << k;
+                }
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    uint32_t phase = 0;
+    if (threadIdx.x == 0 && tile < prm.num_tiles) issue_tile(tile);
+
+    for (; tile < prm.num_tiles; tile += gridDim.x) {
+        const int64_t vid = tile / prm.tiles_per_video;
+        const int ct = (int)(tile - vid * prm.tiles_per_video);
+        const int T = prm.vid_T[vid];
+
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        // ---- shared memory -> registers (transposing loads), then 8x8 bit transposes -----------
+        // P[c][k][m] before the transpose: rows 32 k + 4 m .. + 3 of column c, one per byte
+        uint32_t P[2][NW][8];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                ldsm_x2_trans_b8(P[0][k][2 * j], P[1][k][2 * j], P[0][k][2 * j + 1], P[1][k][2 * j + 1],
+                                 ld_base + (uint32_t)((k * 32 + j * 8) * kStripW));
+        }
+        __syncthreads();                                 // every lane has its columns: buffer is free
+        {
+            const int64_t next = tile + gridDim.x;
+            if (threadIdx.x == 0 && next < prm.num_tiles) {
+                fence_proxy_async();
+                issue_tile(next);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            bit_transpose8(P[0][k]);
+            bit_transpose8(P[1][k]);
+        }
+
+        // ---- alive mask of the last word: bit 8 y + m is row 32 (NW-1) + 4 m + y --------------------
+        uint32_t last_mask = 0u;
+        {
+            const int n = T - 32 * (NW - 1);
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                int cnt = (n - y + 3) >> 2;
+                cnt = cnt < 0 ? 0 : (cnt > 8 ? 8 : cnt);
+                last_mask |= ((1u << cnt) - 1u) << (8 * y);
+            }
+        }
+
+        // ---- 8-pass MSB-first rank select, per column ------------------------------------------------
+        int med[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t alive[NW], alive2[EVEN ? NW : 1];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                alive[k] = k == NW - 1 ? last_mask : 0xFFFFFFFFu;
+                if (EVEN) alive2[k] = alive[k];
+            }
+            int rank = (T - 1) >> 1;                     // 0-based rank of the lower middle among the alive rows
+            int rc = rank - T;                           // rank - (number of alive rows), always negative
+            int lo = 0, hi = 0;
+            int diverged = 0;                            // all-ones once the two middles sit in different sets
+#pragma unroll
+            for (int b = 7; b >= 0; --b) {
+                int d = rc;                              // becomes rank - zeros
+#pragma unroll
+                for (int k = 0; k < NW; ++k) d = popc_acc(alive[k] & P[c][k][b], d, one);
+                uint32_t any0 = 0u;                      // rows of the upper middle's set whose bit is 0
+                if (EVEN) {
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) any0 |= alive2[k] & ~P[c][k][b];
+                }
+                const int m0 = d >> 31;                  // all-ones: rank < zeros, the bit is 0
+                rank = isel(rank, d, m0);
+                rc = isel(d, rc, m0);
+                lo |= ~m0 & (1 << b);
+#pragma unroll
+                for (int k = 0; k < NW; ++k) alive[k] &= P[c][k][b] ^ (uint32_t)m0;
+                if (EVEN) {
+                    // shared state: the upper middle has rank + 1, its bit is 0 iff d + 1 < 0; own state: iff any0
+                    const int m0_shared = (d + 1) >> 31;
+                    const int m0_own = any0 != 0u ? -1 : 0;
+                    const int m2 = isel(m0_own, m0_shared, diverged);
+                    diverged |= m2 ^ m0;
+                    hi |= ~m2 & (1 << b);
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) alive2[k] &= P[c][k][b] ^ (uint32_t)m2;
+                }
+            }
+            med[c] = EVEN ? ((lo + hi) >> 1) : lo;
+        }
+
+        // ---- store ---------------------------------------------------------------------------------------
+        const int64_t col0 = (int64_t)ct * kTileW;
+        uint8_t *dst = prm.out + prm.vid_out[vid] * prm.N + col0;
+        if (col0 + colA < prm.N) dst[colA] = (uint8_t)med[0];
+        if (col0 + colB < prm.N) dst[colB] = (uint8_t)med[1];
+    }
+}
+
+template <int NW, bool EVEN>
+int launch_one(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
+{
+    auto kern = median_ldsm_kernel<NW, EVEN>;
+    BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int blocks_per_sm = 0;
+    BGD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
+    if (blocks_per_sm < 1)
+        return fail(BGD_ERR_CUDA, "median (ldsm): kernel NW=%d does not fit an SM (%zu B smem)", NW, smem);
+    const int64_t cap = (int64_t)sm_count * blocks_per_sm;
+    const int grid = (int)(prm.num_tiles < cap ? prm.num_tiles : cap);
+    kern<<<grid, kThreads, smem, stream>>>(prm);
+    count_launch();
+    BGD_CUDA_TRY(cudaGetLastError());
+    return BGD_OK;
+}
+
+template <int NW>
+int launch_parity(bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
+{
+    return even ? launch_one<NW, true>(prm, sm_count, smem, stream) : launch_one<NW, false>(prm, sm_count, smem, stream);
+}
+#endif  // __CUDACC__
+
+}  // namespace ldsm
+}  // namespace bgd

@@ -35,7 +35,7 @@ def _gpu_median(ops, frames_np):
     return torch.ops.bgdebias.temporal_median(t).cpu().numpy()
 
 
-VARIANTS = {"auto": 0, "swar": 1, "bitsliced": 2, "colplane": 3}
+VARIANTS = {"auto": 0, "swar": 1, "bitsliced": 2, "colplane": 3, "ldsm": 4}
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
@@ -47,7 +47,7 @@ def test_golden_reference_outputs(bgd, name, variant):
     used = frames[mo.select_frame_indices(len(frames), interval, max_frames)]
     N = int(np.prod(used.shape[1:]))
     cabi.set_median_variant(VARIANTS[variant])
-    if variant in ("bitsliced", "colplane") and N % 16 != 0:
+    if variant in ("bitsliced", "colplane", "ldsm") and N % 16 != 0:
         with pytest.raises(cabi.BgdError):
             _gpu_median(ops, used)
         return
@@ -59,11 +59,11 @@ T_VALUES = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 
             179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 527, 528, 543, 544, 576]
 
 
-@pytest.mark.parametrize("variant", ["swar", "bitsliced", "colplane"])
+@pytest.mark.parametrize("variant", ["swar", "bitsliced", "colplane", "ldsm"])
 @pytest.mark.parametrize("T", T_VALUES)
 def test_random_all_T(bgd, T, variant):
     ops, cabi = bgd
-    if (variant == "bitsliced" and T > 528) or (variant == "colplane" and T > 544):
+    if (variant == "bitsliced" and T > 528) or (variant in ("colplane", "ldsm") and T > 544):
         pytest.skip("the TMA variants hold at most ~500 rows per thread group; AUTO falls back to the generic variant")
     cabi.set_median_variant(VARIANTS[variant])
     rng = np.random.default_rng(1000 + T)
@@ -98,7 +98,7 @@ def test_patterns(bgd, pattern, T):
     else:
         fr = np.zeros((T, N), np.uint8)
     exp = mo.temporal_median_np(fr)
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         cabi.set_median_variant(variant)
         np.testing.assert_array_equal(_gpu_median(ops, fr), exp)
 
@@ -123,7 +123,7 @@ def test_varlen_mixed_lengths(bgd):
     fr = rng.integers(0, 256, (int(offs[-1]), N), dtype=np.uint8)
     exp = c_oracle.temporal_median_varlen(fr, offs)
     d = torch.from_numpy(fr).cuda()
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         cabi.set_median_variant(variant)
         got = torch.ops.bgdebias.temporal_median_varlen(d, torch.from_numpy(offs)).cpu().numpy()
         np.testing.assert_array_equal(got, exp)

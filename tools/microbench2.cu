@@ -1,0 +1,332 @@
+// Second probe set for the temporal-median kernel design (sm_100a):
+//   1. does POPC / IMAD.WIDE co-issue beside LOP3 (separate pipes)?
+//   2. fragment layout of ldmatrix.m16n16.trans.b8 (which lane gets which smem rows/bytes)
+//   3. ldmatrix throughput under the row pitches / swizzles the median tile could use
+//   4. TMA 2-D tensor-copy read bandwidth for the tile shapes the kernel could use
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench2 tools/microbench2.cu
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#define CHAINS 8
+#define ITERS 2048
+
+template <int OP>
+__device__ __forceinline__ void step(uint32_t (&a)[CHAINS], uint32_t b, uint32_t c)
+{
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) {
+        if (OP == 0) {   // 4 lop3 + 1 popc : 80/clk if popc has its own pipe, 40/clk if it shares the alu pipe
+            uint32_t t;
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(c), "r"(b));
+            asm volatile("popc.b32 %0, %1;" : "=r"(t) : "r"(a[i]));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(t), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+        }
+        if (OP == 1) {   // mul.wide.u32 alone
+            uint64_t w;
+            asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(a[i]), "r"(0x10000000u));
+            a[i] = (uint32_t)(w >> 32) ^ (uint32_t)w;
+        }
+        if (OP == 2) {   // 2 lop3 + mul.wide (hi and lo both used): transpose pair with one multiply
+            uint32_t lo, hi;
+            asm volatile("{.reg .b64 w; mul.wide.u32 w, %2, %3; mov.b64 {%0, %1}, w;}" : "=r"(lo), "=r"(hi) : "r"(a[i]), "r"(0x10000000u));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE4;" : "+r"(a[i]) : "r"(lo), "r"(b));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xD8;" : "+r"(a[i]) : "r"(hi), "r"(c));
+        }
+        if (OP == 3) {   // 2 lop3 + 1 mul.hi
+            uint32_t t;
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(a[i]), "r"(0x10000000u));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xD8;" : "+r"(a[i]) : "r"(t), "r"(c));
+        }
+        if (OP == 4) {   // 2 lop3 + 1 popc + 1 mad (count accumulation on the fma pipe)
+            uint32_t t;
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("popc.b32 %0, %1;" : "=r"(t) : "r"(a[i]));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(t), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+        }
+        if (OP == 5) {   // 8 lop3 + 1 popc
+            uint32_t t;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("popc.b32 %0, %1;" : "=r"(t) : "r"(a[i]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(t), "r"(c));
+        }
+        if (OP == 6) {   // shf.l.wrap (rotate): same pipe as lop3?
+            asm volatile("shf.l.wrap.b32 %0, %0, %0, %1;" : "+r"(a[i]) : "r"(c & 7));
+        }
+        if (OP == 7) {   // 3 lop3 + 1 imad (the select loop's mix with shifts moved to fma)
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(c), "r"(b));
+        }
+    }
+}
+
+template <int OP>
+__global__ void probe(uint32_t *out, uint32_t b, uint32_t c, long long *cycles)
+{
+    uint32_t a[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) a[i] = threadIdx.x * 2654435761u + i;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 4
+    for (int it = 0; it < ITERS; ++it) step<OP>(a, b, c);
+    const long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(const char *name, int ops_per_step, int sms, uint32_t *d_out, long long *d_cyc)
+{
+    const int threads = 1024, blocks = sms;
+    probe<OP><<<blocks, threads>>>(d_out, 0x9e3779b9u, 0x01010101u, d_cyc);
+    probe<OP><<<blocks, threads>>>(d_out, 0x9e3779b9u, 0x01010101u, d_cyc);
+    cudaDeviceSynchronize();
+    long long cyc[1024];
+    cudaMemcpy(cyc, d_cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
+    double mean = 0; for (int i = 0; i < blocks; ++i) mean += cyc[i]; mean /= blocks;
+    const double ops = (double)threads * CHAINS * ITERS * ops_per_step;
+    printf("%-44s %8.1f thread-ops/clk/SM\n", name, ops / mean);
+}
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- 2. ldmatrix.m16n16.trans.b8 fragment layout -------------------------------------------
+__global__ void ldsm_layout(uint32_t *out)
+{
+    __shared__ __align__(128) uint8_t sm[512];
+    for (int i = threadIdx.x; i < 512; i += 32) sm[i] = (uint8_t)i;    // matrix 0: bytes 0..255 (row r = bytes 16r..16r+15), matrix 1: same + 256
+    __syncwarp();
+    uint32_t r0, r1, r2, r3;
+    const uint32_t addr = s32(sm + (threadIdx.x & 15) * 16 + (threadIdx.x >> 4) * 256);
+    asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+    out[threadIdx.x * 4 + 0] = r0; out[threadIdx.x * 4 + 1] = r1;
+    out[threadIdx.x * 4 + 2] = r2; out[threadIdx.x * 4 + 3] = r3;
+}
+
+// ---- 3. ldmatrix throughput ------------------------------------------------------------------
+// MODE 0: pitch 256, no swizzle, column chunks {0,1,2,3}+4*(warp&3)   (4-way bank conflict expected)
+// MODE 1: pitch 128, 128B swizzle (chunk ^= row & 7), chunks {0,4,1,5} / {2,6,3,7} (conflict free)
+// MODE 2: pitch 128, 128B swizzle, chunks {0,1,2,3} / {4,5,6,7}
+// MODE 3: plain LDS.32 strided like the current kernel's C=4 path (pitch 256): reference point
+template <int MODE>
+__global__ void ldsm_tput(uint32_t *out, long long *cycles, int rows)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    for (int i = threadIdx.x; i < rows * 256; i += blockDim.x) smem[i] = (uint8_t)(i * 7);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = lane & 15, mat = lane >> 4, q = a >> 2, i = a & 3;
+    uint32_t acc = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < 64; ++it) {
+#pragma unroll 4
+        for (int r0 = 0; r0 + 8 <= rows; r0 += 8) {
+            const int row = r0 + 4 * mat + i;
+            uint32_t addr;
+            if (MODE == 0) addr = s32(smem) + row * 256 + (q + 4 * (warp & 3)) * 16;
+            else if (MODE == 1) {
+                const int cb = ((q & 1) * 4 + (q >> 1)) + 2 * (warp & 1);
+                addr = s32(smem) + (warp >> 1 & 1) * rows * 128 + row * 128 + ((cb ^ (row & 7)) * 16);
+            } else if (MODE == 2) {
+                const int cb = q + 4 * (warp & 1);
+                addr = s32(smem) + (warp >> 1 & 1) * rows * 128 + row * 128 + ((cb ^ (row & 7)) * 16);
+            } else addr = s32(smem) + (r0 + (lane >> 3)) * 256 + (warp & 1) * 128 + (lane & 7) * 4;   // unused layout for MODE 3
+            uint32_t x0, x1, x2, x3;
+            if (MODE < 3) {
+                asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+            } else {
+                const uint32_t base = s32(smem) + r0 * 256 + (threadIdx.x & 63) * 4;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(base));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(base + 256));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x2) : "r"(base + 512));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x3) : "r"(base + 768));
+            }
+            acc ^= x0 ^ x1 ^ x2 ^ x3;
+        }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE>
+void run_ldsm(const char *name, int sms, uint32_t *d_out, long long *d_cyc)
+{
+    const int rows = 192, threads = 256;
+    const size_t smem = (size_t)rows * 256;
+    cudaFuncSetAttribute(ldsm_tput<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ldsm_tput<MODE><<<sms, threads, smem>>>(d_out, d_cyc, rows);
+    ldsm_tput<MODE><<<sms, threads, smem>>>(d_out, d_cyc, rows);
+    cudaDeviceSynchronize();
+    long long cyc[1024];
+    cudaMemcpy(cyc, d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    double mean = 0; for (int i = 0; i < sms; ++i) mean += cyc[i]; mean /= sms;
+    const double bytes = 64.0 * (rows / 8) * (threads / 32) * 512;
+    printf("%-60s %7.1f B/clk/SM  (%s)\n", name, bytes / mean, cudaGetErrorString(cudaGetLastError()));
+}
+
+// ---- 4. TMA tensor-copy read bandwidth -----------------------------------------------------------
+struct alignas(64) TParams {
+    CUtensorMap map;
+    int64_t num_tiles;
+    int32_t tiles_per_video, rows, strips, strip_w, stages;
+};
+
+__global__ void tma_read(const __grid_constant__ TParams prm, uint32_t *sink)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tile_bytes = prm.rows * prm.strips * prm.strip_w;
+    const int stage_stride = (tile_bytes + 1023) & ~1023;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)prm.stages * stage_stride);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < prm.stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar + s)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile, int slot) {
+        const int64_t vid = tile / prm.tiles_per_video;
+        const int ct = (int)(tile - vid * prm.tiles_per_video);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar + slot)), "r"((uint32_t)tile_bytes) : "memory");
+        for (int s = 0; s < prm.strips; ++s)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(s32(smem + (size_t)slot * stage_stride + (size_t)s * prm.rows * prm.strip_w)),
+                         "l"(reinterpret_cast<uint64_t>(&prm.map)), "r"((ct * prm.strips + s) * prm.strip_w), "r"((int)(vid * prm.rows)),
+                         "r"(s32(bar + slot)) : "memory");
+    };
+    uint32_t acc = 0;
+    uint32_t phase = 0;   // bit s = parity of stage s
+    int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        if (prm.stages == 1 && tile < prm.num_tiles) issue(tile, 0);
+        for (int s = 0; s < prm.stages - 1 && tile + (int64_t)s * gridDim.x < prm.num_tiles; ++s) issue(tile + (int64_t)s * gridDim.x, s);
+    }
+    int slot = 0;
+    for (; tile < prm.num_tiles; tile += gridDim.x) {
+        const int64_t nxt = tile + (int64_t)(prm.stages - 1) * gridDim.x;
+        const int nslot = (slot + prm.stages - 1) % prm.stages;
+        if (prm.stages > 1 && threadIdx.x == 0 && nxt < prm.num_tiles) issue(nxt, nslot);
+        asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n"
+                     ::"r"(s32(bar + slot)), "r"((phase >> slot) & 1u) : "memory");
+        phase ^= 1u << slot;
+        acc ^= reinterpret_cast<uint32_t *>(smem + (size_t)slot * stage_stride)[threadIdx.x];
+        __syncthreads();
+        if (prm.stages == 1 && threadIdx.x == 0 && tile + gridDim.x < prm.num_tiles) issue(tile + gridDim.x, 0);
+        slot = (slot + 1) % prm.stages;
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main()
+{
+    setvbuf(stdout, nullptr, _IONBF, 0);
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount;
+    printf("device %s, %d SMs, cc %d.%d\n", p.name, sms, p.major, p.minor);
+    uint32_t *d_out; long long *d_cyc;
+    cudaMalloc(&d_out, sizeof(uint32_t) * 1024 * sms);
+    cudaMalloc(&d_cyc, sizeof(long long) * sms);
+    if (!getenv("MB_SKIP_PIPES")) {
+    run<0>("4 lop3 + 1 popc (80 = own pipe, 40 = shared)", 5, sms, d_out, d_cyc);
+    run<5>("8 lop3 + 1 popc (72 = own pipe, 48 = shared)", 9, sms, d_out, d_cyc);
+    run<1>("mul.wide.u32", 1, sms, d_out, d_cyc);
+    run<2>("2 lop3 + mul.wide", 3, sms, d_out, d_cyc);
+    run<3>("2 lop3 + mul.hi", 3, sms, d_out, d_cyc);
+    run<4>("2 lop3 + popc + mad", 4, sms, d_out, d_cyc);
+    run<6>("shf.l.wrap", 1, sms, d_out, d_cyc);
+    run<7>("3 lop3 + 1 imad", 4, sms, d_out, d_cyc);
+
+    {
+        ldsm_layout<<<1, 32>>>(d_out);
+        uint32_t h[128];
+        cudaMemcpy(h, d_out, 512, cudaMemcpyDeviceToHost);
+        printf("ldmatrix.m16n16.x2.trans.b8: smem byte = 16*row + col (+256 for matrix 1); regs little-endian bytes\n");
+        for (int i = 0; i < 32; ++i) {
+            printf(" lane %2d:", i);
+            for (int r = 0; r < 4; ++r) {
+                printf("  r%d=", r);
+                for (int b = 0; b < 4; ++b) {
+                    const int v = (h[4 * i + r] >> (8 * b)) & 255;
+                    printf("(%2d,%2d)", v >> 4, v & 15);
+                }
+            }
+            printf("\n");
+        }
+    }
+    }
+    run_ldsm<0>("ldmatrix x2, pitch 256, no swizzle", sms, d_out, d_cyc);
+    run_ldsm<1>("ldmatrix x2, pitch 128, swizzle128, chunks {0,4,1,5}", sms, d_out, d_cyc);
+    run_ldsm<2>("ldmatrix x2, pitch 128, swizzle128, chunks {0,1,2,3}", sms, d_out, d_cyc);
+    run_ldsm<3>("ld.shared.b32 x4, pitch 256", sms, d_out, d_cyc);
+
+    if (getenv("MB_NO_BW")) return 0;
+    EncodeTiledFn encode = nullptr;
+    {
+        void *fp = nullptr; cudaDriverEntryPointQueryResult q;
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
+        encode = reinterpret_cast<EncodeTiledFn>(fp);
+        if (!encode) { printf("no cuTensorMapEncodeTiled\n"); return 1; }
+    }
+    const int64_t N = 230400;
+    const int V = 128;
+    uint32_t *d_sink; cudaMalloc(&d_sink, 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // {strip_w, swizzle(0 none,1 =128B), strips, rows, stages, ctas_per_sm}
+    const int cfgs[][6] = {
+        {256, 0, 1, 181, 1, 4}, {256, 0, 1, 181, 2, 2}, {256, 0, 2, 181, 1, 2}, {256, 0, 2, 181, 2, 1},
+        {128, 1, 2, 181, 1, 4}, {128, 1, 2, 181, 2, 2}, {128, 1, 1, 181, 2, 4}, {128, 1, 4, 181, 2, 1},
+        {128, 1, 4, 181, 1, 2}, {256, 0, 1, 240, 1, 3}, {128, 1, 2, 240, 1, 3}, {128, 1, 2, 64, 2, 4}, {256, 0, 1, 64, 2, 4},
+        {128, 1, 2, 181, 3, 1}, {256, 0, 1, 181, 3, 1}, {128, 1, 1, 181, 1, 8}, {128, 1, 1, 181, 2, 5},
+    };
+    uint8_t *d_src;
+    cudaMalloc(&d_src, (size_t)V * 240 * N); cudaMemset(d_src, 1, (size_t)V * 240 * N);
+    for (auto &c : cfgs) {
+        const int strip_w = c[0], swz = c[1], strips = c[2], rows = c[3], stages = c[4], ctas = c[5];
+        TParams prm{};
+        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)V * rows};
+        const cuuint64_t gstride[1] = {(cuuint64_t)N};
+        const cuuint32_t box[2] = {(cuuint32_t)strip_w, (cuuint32_t)rows};
+        const cuuint32_t estride[2] = {1, 1};
+        const CUresult r = encode(&prm.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_src, gdim, gstride, box, estride,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+        const int tile_w = strip_w * strips;
+        prm.tiles_per_video = (int)(N / tile_w);
+        prm.num_tiles = (int64_t)V * prm.tiles_per_video;
+        prm.rows = rows; prm.strips = strips; prm.strip_w = strip_w; prm.stages = stages;
+        const size_t smem = (size_t)stages * (((size_t)rows * tile_w + 1023) & ~(size_t)1023) + 64;
+        cudaFuncSetAttribute(tma_read, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        float best = 1e9f;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0);
+            tma_read<<<sms * ctas, 128, smem>>>(prm, d_sink);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        printf("TMA 2-D box %3d B x %3d rows%s, %d strips/tile, %d stages, %d CTA/SM (%6zu B smem): %8.1f GB/s  (%s)\n", strip_w, rows,
+               swz ? " swizzle128" : "           ", strips, stages, ctas, smem, (double)V * rows * prm.tiles_per_video * tile_w / (best * 1e6),
+               cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
