@@ -25,6 +25,7 @@ struct Tuning {
     int t_c4 = 96;     // T <= t_c4: 4 columns per thread (8 rows per plane word)
     int t_c2 = 240;    // T <= t_c2: 2 columns per thread (16 rows per plane word)
     int threads_c1 = 256, threads_c2 = 128, threads_c4 = 128;
+    int ldsm_strips = 1;   // 128-byte strips per CTA tile of the transposing-load kernel
 };
 
 Tuning read_tuning()
@@ -32,6 +33,7 @@ Tuning read_tuning()
     Tuning t;
     if (const char *s = getenv("BGD_COL_T_C4")) t.t_c4 = atoi(s);
     if (const char *s = getenv("BGD_COL_T_C2")) t.t_c2 = atoi(s);
+    if (const char *s = getenv("BGD_LDSM_STRIPS")) t.ldsm_strips = atoi(s) >= 2 ? 2 : 1;
     if (const char *s = getenv("BGD_COL_THREADS_C2")) t.threads_c2 = atoi(s) >= 256 ? 256 : 128;
     if (const char *s = getenv("BGD_COL_THREADS_C4")) { const int v = atoi(s); t.threads_c4 = v >= 256 ? 256 : (v >= 192 ? 192 : (v >= 128 ? 128 : 64)); }
     return t;
@@ -166,12 +168,14 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
             lprm.vid_T = d_T + pos;
             lprm.vid_out = d_outi + pos;
             lprm.N = N;
-            lprm.tiles_per_video = (int32_t)((N + ldsm::kTileW - 1) / ldsm::kTileW);
+            lprm.strips = tn.ldsm_strips;
+            const int tile_w = lprm.strips * ldsm::kStripW;
+            lprm.tiles_per_video = (int32_t)((N + tile_w - 1) / tile_w);
             lprm.num_tiles = nv * lprm.tiles_per_video;
             lprm.rows_cap = key.NW * 32;
             lprm.one = 1u;
             // tile + mbarrier + slack to align the tile to the 1024-byte swizzle atom
-            const size_t smem = (size_t)lprm.rows_cap * ldsm::kTileW + 16 + 1024;
+            const size_t smem = (size_t)lprm.rows_cap * tile_w + 16 + 1024;
             rc = ldsm::launch(key.NW, key.even != 0, lprm, dp.sm_count, smem, stream);
             if (rc) break;
             pos += nv;

@@ -36,9 +36,8 @@
 namespace bgd {
 namespace ldsm {
 
-constexpr int kThreads = 128;
-constexpr int kTileW = 256;               // bytes per tile row
-constexpr int kStripW = 128;              // bytes per TMA strip (= the 128-byte swizzle span)
+constexpr int kStripW = 128;              // bytes per TMA strip (= the 128-byte swizzle span); 2 warps per strip
+constexpr int kMaxStrips = 2;             // a CTA tile is 1 or 2 strips wide
 constexpr int kMaxNW = 8;                 // T <= 256
 
 struct alignas(64) LParams {
@@ -52,6 +51,7 @@ struct alignas(64) LParams {
     int32_t tiles_per_video;
     int32_t rows_cap;            // smem rows per strip (= NW * 32)
     uint32_t one;                // 1, opaque to the compiler: keeps count accumulation on IMAD
+    int32_t strips;              // strips per CTA tile (1 or 2): tile width = 128 * strips, block = 64 * strips threads
 };
 
 int launch(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);
@@ -93,11 +93,12 @@ __device__ __forceinline__ int isel(int a, int b, int mask)
     return d;
 }
 
-template <int NW> constexpr int min_blocks() { return NW <= 6 ? 4 : 3; }
+template <int NW, int STRIPS> constexpr int min_blocks() { return (NW <= 6 ? 8 : 6) / STRIPS; }
 
-template <int NW, bool EVEN>
-__global__ void __launch_bounds__(kThreads, min_blocks<NW>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
+template <int NW, bool EVEN, int STRIPS>
+__global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
 {
+    constexpr int kTileW = STRIPS * kStripW;
     extern __shared__ uint8_t smem_raw[];
     // the 128-byte swizzle pattern repeats every 1024 bytes of shared-memory address: align the tile to it
     uint8_t *buf = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -247,10 +248,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks<NW>()) median_ldsm_kernel
     }
 }
 
-template <int NW, bool EVEN>
-int launch_one(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
+template <int NW, bool EVEN, int STRIPS>
+int launch_strips(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
 {
-    auto kern = median_ldsm_kernel<NW, EVEN>;
+    constexpr int kThreads = 64 * STRIPS;
+    auto kern = median_ldsm_kernel<NW, EVEN, STRIPS>;
     BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int blocks_per_sm = 0;
@@ -263,6 +265,13 @@ int launch_one(const LParams &prm, int sm_count, size_t smem, cudaStream_t strea
     count_launch();
     BGD_CUDA_TRY(cudaGetLastError());
     return BGD_OK;
+}
+
+template <int NW, bool EVEN>
+int launch_one(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
+{
+    return prm.strips == 2 ? launch_strips<NW, EVEN, 2>(prm, sm_count, smem, stream)
+                           : launch_strips<NW, EVEN, 1>(prm, sm_count, smem, stream);
 }
 
 template <int NW>

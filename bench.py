@@ -352,7 +352,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "configs[1]: UCF101-shaped set, one 1/8 shard per GPU", "videos_per_gpu": V,
                        "frames_per_gpu": rows, "frame_shape": [H, W, 3], "T": "U[120,240]", "resident_gb": rows * N_BYTES / 1e9,
-                       "l2": "inputs (>60 GB per GPU) exceed L2; no flush needed", "kernel": "median_colplane (AUTO)",
+                       "l2": "inputs (>60 GB per GPU) exceed L2; no flush needed", "kernel": "median_ldsm for T<=256, median_colplane above (AUTO)",
                        "parallelism": f"shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": rows_e * N_BYTES,
                     "d2h_bytes_per_step": Ve * N_BYTES, "videos_per_step": Ve, "parity": e2e_ok},

@@ -291,7 +291,8 @@ int main()
     uint32_t *d_sink; cudaMalloc(&d_sink, 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     // {strip_w, swizzle(0 none,1 =128B), strips, rows, stages, ctas_per_sm}
-    const int cfgs[][6] = {
+    const int cfgs[][7] = {
+        {64, 2, 1, 181, 1, 16, 32}, {64, 2, 1, 181, 2, 8, 32}, {64, 2, 1, 181, 1, 8, 32}, {64, 0, 1, 181, 1, 16, 32}, {128, 1, 1, 181, 1, 8, 64}, {64, 2, 1, 64, 2, 16, 32}, {64, 2, 1, 240, 1, 12, 32}, {64, 2, 4, 181, 1, 4, 128},
         {256, 0, 1, 181, 1, 4}, {256, 0, 1, 181, 2, 2}, {256, 0, 2, 181, 1, 2}, {256, 0, 2, 181, 2, 1},
         {128, 1, 2, 181, 1, 4}, {128, 1, 2, 181, 2, 2}, {128, 1, 1, 181, 2, 4}, {128, 1, 4, 181, 2, 1},
         {128, 1, 4, 181, 1, 2}, {256, 0, 1, 240, 1, 3}, {128, 1, 2, 240, 1, 3}, {128, 1, 2, 64, 2, 4}, {256, 0, 1, 64, 2, 4},
@@ -300,14 +301,14 @@ int main()
     uint8_t *d_src;
     cudaMalloc(&d_src, (size_t)V * 240 * N); cudaMemset(d_src, 1, (size_t)V * 240 * N);
     for (auto &c : cfgs) {
-        const int strip_w = c[0], swz = c[1], strips = c[2], rows = c[3], stages = c[4], ctas = c[5];
+        const int strip_w = c[0], swz = c[1], strips = c[2], rows = c[3], stages = c[4], ctas = c[5], threads = c[6] ? c[6] : 128;
         TParams prm{};
         const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)V * rows};
         const cuuint64_t gstride[1] = {(cuuint64_t)N};
         const cuuint32_t box[2] = {(cuuint32_t)strip_w, (cuuint32_t)rows};
         const cuuint32_t estride[2] = {1, 1};
         const CUresult r = encode(&prm.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_src, gdim, gstride, box, estride,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
         const int tile_w = strip_w * strips;
@@ -319,13 +320,13 @@ int main()
         float best = 1e9f;
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(e0);
-            tma_read<<<sms * ctas, 128, smem>>>(prm, d_sink);
+            tma_read<<<sms * ctas, threads, smem>>>(prm, d_sink);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             if (rep && ms < best) best = ms;
         }
-        printf("TMA 2-D box %3d B x %3d rows%s, %d strips/tile, %d stages, %d CTA/SM (%6zu B smem): %8.1f GB/s  (%s)\n", strip_w, rows,
-               swz ? " swizzle128" : "           ", strips, stages, ctas, smem, (double)V * rows * prm.tiles_per_video * tile_w / (best * 1e6),
+        printf("TMA 2-D box %3d B x %3d rows%s, %d strips/tile, %d stages, %d CTA/SM x %d thr (%6zu B smem): %8.1f GB/s  (%s)\n", strip_w, rows,
+               swz == 1 ? " swizzle128" : (swz == 2 ? " swizzle64 " : "           "), strips, stages, ctas, threads, smem, (double)V * rows * prm.tiles_per_video * tile_w / (best * 1e6),
                cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
