@@ -52,6 +52,7 @@ int get_device_props(int device, DeviceProps *out)
     d.cc_major = p.major;
     d.cc_minor = p.minor;
     d.smem_optin = (int64_t)p.sharedMemPerBlockOptin;
+    d.smem_per_sm = (int64_t)p.sharedMemPerMultiprocessor;
     d.total_mem = (int64_t)p.totalGlobalMem;
     d.ok = true;
     if (device < 64) cache[device] = d;

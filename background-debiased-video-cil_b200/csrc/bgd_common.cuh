@@ -34,6 +34,7 @@ struct DeviceProps {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     int64_t smem_optin = 0;
+    int64_t smem_per_sm = 0;
     int64_t total_mem = 0;
     bool ok = false;
 };

@@ -25,7 +25,9 @@ struct Tuning {
     int t_c4 = 96;     // T <= t_c4: 4 columns per thread (8 rows per plane word)
     int t_c2 = 240;    // T <= t_c2: 2 columns per thread (16 rows per plane word)
     int threads_c1 = 256, threads_c2 = 128, threads_c4 = 128;
-    int ldsm_strips = 1;   // 128-byte strips per CTA tile of the transposing-load kernel
+    int ldsm_strips = 0;   // 128-byte strips per CTA tile of the transposing-load kernel; 0 = by parity (see below)
+    int ldsm_stages = 0;   // tile buffers per CTA; 0 = as many (up to 4) as fit beside the target CTA count
+    int ldsm_blocks = 0;   // CTAs per SM; 0 = register limit (8 / strips for T <= 192, 6 / strips above)
 };
 
 Tuning read_tuning()
@@ -33,7 +35,9 @@ Tuning read_tuning()
     Tuning t;
     if (const char *s = getenv("BGD_COL_T_C4")) t.t_c4 = atoi(s);
     if (const char *s = getenv("BGD_COL_T_C2")) t.t_c2 = atoi(s);
-    if (const char *s = getenv("BGD_LDSM_STRIPS")) t.ldsm_strips = atoi(s) >= 2 ? 2 : 1;
+    if (const char *s = getenv("BGD_LDSM_STRIPS")) { const int v = atoi(s); t.ldsm_strips = v >= 4 ? 4 : (v >= 2 ? 2 : (v == 1 ? 1 : 0)); }
+    if (const char *s = getenv("BGD_LDSM_STAGES")) t.ldsm_stages = std::max(0, std::min(8, atoi(s)));
+    if (const char *s = getenv("BGD_LDSM_BLOCKS")) t.ldsm_blocks = std::max(0, atoi(s));
     if (const char *s = getenv("BGD_COL_THREADS_C2")) t.threads_c2 = atoi(s) >= 256 ? 256 : 128;
     if (const char *s = getenv("BGD_COL_THREADS_C4")) { const int v = atoi(s); t.threads_c4 = v >= 256 ? 256 : (v >= 192 ? 192 : (v >= 128 ? 128 : 64)); }
     return t;
@@ -168,14 +172,29 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
             lprm.vid_T = d_T + pos;
             lprm.vid_out = d_outi + pos;
             lprm.N = N;
-            lprm.strips = tn.ldsm_strips;
+            // long odd videos run close to the HBM limit and gain from wider rows per copy (+8 % at T = 181);
+            // even T (bound by the LOP3 pipe) and short videos gain from the finer-grained CTAs (+3..6 %)
+            // (profiles/r1_sweep_ldsm_strips.txt)
+            lprm.strips = tn.ldsm_strips > 0 ? tn.ldsm_strips : ((!key.even && key.NW >= 5) ? 2 : 1);
             const int tile_w = lprm.strips * ldsm::kStripW;
             lprm.tiles_per_video = (int32_t)((N + tile_w - 1) / tile_w);
             lprm.num_tiles = nv * lprm.tiles_per_video;
+            if (lprm.num_tiles >= ((int64_t)1 << 31)) {
+                rc = fail(BGD_ERR_UNSUPPORTED, "median (ldsm): %lld tiles in one call; split the batch", (long long)lprm.num_tiles);
+                break;
+            }
             lprm.rows_cap = key.NW * 32;
             lprm.one = 1u;
-            // tile + mbarrier + slack to align the tile to the 1024-byte swizzle atom
-            const size_t smem = (size_t)lprm.rows_cap * tile_w + 16 + 1024;
+            // buffers + mbarriers + slack to align the buffers to the 1024-byte swizzle atom; as many stages as
+            // fit beside the CTA count the registers allow (1 KB per CTA is reserved by the driver)
+            const size_t tile_bytes = (size_t)lprm.rows_cap * tile_w;
+            const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks : (key.NW <= 6 ? 8 : 6) / lprm.strips;
+            const size_t per_block = (size_t)dp.smem_per_sm / blocks - 1024;
+            int stages = tn.ldsm_stages > 0 ? tn.ldsm_stages : (int)((per_block - 1024 - 64) / tile_bytes);
+            stages = std::max(1, std::min(stages, tn.ldsm_stages > 0 ? 8 : 4));
+            lprm.stages = stages;
+            lprm.max_blocks_per_sm = blocks;
+            const size_t smem = (size_t)stages * tile_bytes + 64 + 1024;
             rc = ldsm::launch(key.NW, key.even != 0, lprm, dp.sm_count, smem, stream);
             if (rc) break;
             pos += nv;

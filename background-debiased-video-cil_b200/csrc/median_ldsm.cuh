@@ -37,7 +37,7 @@ namespace bgd {
 namespace ldsm {
 
 constexpr int kStripW = 128;              // bytes per TMA strip (= the 128-byte swizzle span); 2 warps per strip
-constexpr int kMaxStrips = 2;             // a CTA tile is 1 or 2 strips wide
+constexpr int kMaxStrips = 4;             // a CTA tile is 1, 2 or 4 strips wide
 constexpr int kMaxNW = 8;                 // T <= 256
 
 struct alignas(64) LParams {
@@ -51,7 +51,9 @@ struct alignas(64) LParams {
     int32_t tiles_per_video;
     int32_t rows_cap;            // smem rows per strip (= NW * 32)
     uint32_t one;                // 1, opaque to the compiler: keeps count accumulation on IMAD
-    int32_t strips;              // strips per CTA tile (1 or 2): tile width = 128 * strips, block = 64 * strips threads
+    int32_t strips;              // strips per CTA tile (1, 2 or 4): tile width = 128 * strips, block = 64 * strips threads
+    int32_t stages;              // tile buffers per CTA (ring); tile i of a CTA lives in buffer i % stages
+    int32_t max_blocks_per_sm;   // 0 = as many as fit
 };
 
 int launch(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);
@@ -93,6 +95,14 @@ __device__ __forceinline__ int isel(int a, int b, int mask)
     return d;
 }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int NW, int STRIPS> constexpr int min_blocks() { return (NW <= 6 ? 8 : 6) / STRIPS; }
 
 template <int NW, bool EVEN, int STRIPS>
@@ -102,7 +112,9 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
     extern __shared__ uint8_t smem_raw[];
     // the 128-byte swizzle pattern repeats every 1024 bytes of shared-memory address: align the tile to it
     uint8_t *buf = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(buf + (size_t)prm.rows_cap * kTileW);
+    const int stages = prm.stages;
+    const uint32_t stage_bytes = (uint32_t)prm.rows_cap * kTileW;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(buf + (size_t)stages * stage_bytes);   // bar[s]: buffer s is full
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t one = prm.one;
 
@@ -117,48 +129,70 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
     const int colA = (warp >> 1) * kStripW + chunk_of(lane & 3) * 16 + (lane >> 2), colB = colA + 8;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+        for (int s = 0; s < stages; ++s) mbar_init(bar + s, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
+    // tiles are numbered video-major; a CTA walks tile, tile + grid, ...: (video, column tile) advance by a
+    // fixed step with one carry, no division in the loop (num_tiles < 2^31 is checked on the host)
+    const int tpv = prm.tiles_per_video, num_tiles = (int)prm.num_tiles;
+    const int step_vid = (int)gridDim.x / tpv, step_ct = (int)gridDim.x - step_vid * tpv;
+    auto advance = [&](int &t, int &v, int &c) {
+        t += (int)gridDim.x;
+        v += step_vid;
+        c += step_ct;
+        if (c >= tpv) {
+            c -= tpv;
+            ++v;
+        }
+    };
+
+    const bool producer = warp == 0 && elect_one();      // one lane of warp 0 issues the TMA copies
     uint64_t policy = 0;
-    if (threadIdx.x == 0) policy = policy_evict_first();
-    auto issue_tile = [&](int64_t tile) {                // thread 0 only
-        const int64_t vid = tile / prm.tiles_per_video;
-        const int ct = (int)(tile - vid * prm.tiles_per_video);
-        const int T = prm.vid_T[vid];
-        const int64_t row0 = prm.vid_row0[vid];
-        mbar_arrive_expect_tx(bar, (uint32_t)T * (uint32_t)kTileW);
+    if (producer) policy = policy_evict_first();
+    // Called by all lanes of warp 0 (the table reads are broadcast with SHFL so that ptxas sees warp-uniform
+    // TMA operands and moves them to uniform registers without a per-value loop); the producer lane issues.
+    auto issue_tile = [&](int vid, int ct, int slot) {
+        uint64_t *bar_s = bar + slot;
+        uint8_t *buf_s = buf + (size_t)slot * stage_bytes;
+        const int T = __shfl_sync(0xFFFFFFFFu, prm.vid_T[vid], 0);
+        const int row0 = __shfl_sync(0xFFFFFFFFu, (int)prm.vid_row0[vid], 0);
+        if (!producer) return;
+        mbar_arrive_expect_tx(bar_s, (uint32_t)T * (uint32_t)kTileW);
 #pragma unroll
         for (int s = 0; s < kTileW / kStripW; ++s) {
             const int col = ct * kTileW + s * kStripW;
-            uint8_t *dst = buf + (size_t)s * strip_bytes;
+            uint8_t *dst = buf_s + (size_t)s * strip_bytes;
             int r = 0;
             if (T >= 256) {
-                tma_load_2d(dst, &prm.maps[8], col, (int)row0, bar, policy);
+                tma_load_2d(dst, &prm.maps[8], col, (int)row0, bar_s, policy);
                 r = 256;
             }
 #pragma unroll
             for (int k = 7; k >= 0; --k)
                 if ((T - r) & (1 << k)) {
-                    tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[k], col, (int)(row0 + r), bar, policy);
+                    tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[k], col, (int)(row0 + r), bar_s, policy);
                     r += 1 << k;
                 }
         }
     };
 
-    int64_t tile = blockIdx.x;
-    uint32_t phase = 0;
-    if (threadIdx.x == 0 && tile < prm.num_tiles) issue_tile(tile);
+    int tile = blockIdx.x, vid = tile / tpv, ct = tile - vid * tpv;
+    int ptile = tile, pvid = vid, pct = ct;              // the producer's cursor: `stages` tiles ahead
+    for (int s = 0; s < stages; ++s) {
+        if (warp == 0 && ptile < num_tiles) issue_tile(pvid, pct, s);
+        advance(ptile, pvid, pct);
+    }
 
-    for (; tile < prm.num_tiles; tile += gridDim.x) {
-        const int64_t vid = tile / prm.tiles_per_video;
-        const int ct = (int)(tile - vid * prm.tiles_per_video);
+    int slot = 0;
+    uint32_t phases = 0;                                 // bit s: parity to wait for on bar[s]
+    for (; tile < num_tiles; advance(tile, vid, ct)) {
         const int T = prm.vid_T[vid];
 
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        mbar_wait(bar + slot, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        const uint32_t ld_slot = ld_base + (uint32_t)slot * stage_bytes;
 
         // ---- shared memory -> registers (transposing loads), then 8x8 bit transposes -----------
         // P[c][k][m] before the transpose: rows 32 k + 4 m .. + 3 of column c, one per byte
@@ -168,15 +202,16 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 ldsm_x2_trans_b8(P[0][k][2 * j], P[1][k][2 * j], P[0][k][2 * j + 1], P[1][k][2 * j + 1],
-                                 ld_base + (uint32_t)((k * 32 + j * 8) * kStripW));
+                                 ld_slot + (uint32_t)((k * 32 + j * 8) * kStripW));
         }
         __syncthreads();                                 // every lane has its columns: buffer is free
         {
-            const int64_t next = tile + gridDim.x;
-            if (threadIdx.x == 0 && next < prm.num_tiles) {
-                fence_proxy_async();
-                issue_tile(next);
+            if (warp == 0 && ptile < num_tiles) {
+                if (producer) fence_proxy_async();
+                issue_tile(pvid, pct, slot);
             }
+            advance(ptile, pvid, pct);
+            slot = slot + 1 == stages ? 0 : slot + 1;
         }
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
@@ -259,6 +294,7 @@ int launch_strips(const LParams &prm, int sm_count, size_t smem, cudaStream_t st
     BGD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
     if (blocks_per_sm < 1)
         return fail(BGD_ERR_CUDA, "median (ldsm): kernel NW=%d does not fit an SM (%zu B smem)", NW, smem);
+    if (prm.max_blocks_per_sm > 0 && blocks_per_sm > prm.max_blocks_per_sm) blocks_per_sm = prm.max_blocks_per_sm;
     const int64_t cap = (int64_t)sm_count * blocks_per_sm;
     const int grid = (int)(prm.num_tiles < cap ? prm.num_tiles : cap);
     kern<<<grid, kThreads, smem, stream>>>(prm);
@@ -270,8 +306,9 @@ int launch_strips(const LParams &prm, int sm_count, size_t smem, cudaStream_t st
 template <int NW, bool EVEN>
 int launch_one(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
 {
-    return prm.strips == 2 ? launch_strips<NW, EVEN, 2>(prm, sm_count, smem, stream)
-                           : launch_strips<NW, EVEN, 1>(prm, sm_count, smem, stream);
+    return prm.strips == 4 ? launch_strips<NW, EVEN, 4>(prm, sm_count, smem, stream)
+           : prm.strips == 2 ? launch_strips<NW, EVEN, 2>(prm, sm_count, smem, stream)
+                             : launch_strips<NW, EVEN, 1>(prm, sm_count, smem, stream);
 }
 
 template <int NW>
