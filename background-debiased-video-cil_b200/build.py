@@ -20,8 +20,8 @@ OBJ = CSRC / ("_obj" + ("_" + os.environ["BGD_BUILD_OUT"].replace(".", "_") if o
 LIB = PKG / os.environ.get("BGD_BUILD_OUT", "libbgdebias_b200.so")
 EXTRA_DEFINES = [d for d in os.environ.get("BGD_BUILD_DEFINES", "").split() if d]
 SOURCES = ["api.cu", "median_swar.cu", "median_bitsliced.cu", "median_colplane.cu", "median_colplane_c1.cu",
-           "median_colplane_c2.cu", "median_colplane_c4.cu", "median_ldsm_lo.cu", "median_ldsm_mid.cu",
-           "median_ldsm_hi.cu", "bgmix.cu"]
+           "median_colplane_c2.cu", "median_colplane_c4.cu", "median_ldsm_q0.cu", "median_ldsm_q1.cu",
+           "median_ldsm_q2.cu", "median_ldsm_q3.cu", "bgmix.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

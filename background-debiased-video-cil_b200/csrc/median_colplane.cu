@@ -17,7 +17,7 @@ using colplane::kNumMaps;
 using colplane::kStripBytes;
 
 struct Key {
-    int C, NW, even;   // C == 0: the transposing-load kernel (median_ldsm.cuh), 2 columns per lane, 32 rows per word
+    int C, NW, even;   // C == 0: the transposing-load kernel (median_ldsm.cuh); NW then counts half groups of 16 rows
     bool operator<(const Key &o) const { return std::tie(C, NW, even) < std::tie(o.C, o.NW, o.even); }
 };
 
@@ -35,7 +35,7 @@ Tuning read_tuning()
     Tuning t;
     if (const char *s = getenv("BGD_COL_T_C4")) t.t_c4 = atoi(s);
     if (const char *s = getenv("BGD_COL_T_C2")) t.t_c2 = atoi(s);
-    if (const char *s = getenv("BGD_LDSM_STRIPS")) { const int v = atoi(s); t.ldsm_strips = v >= 4 ? 4 : (v >= 2 ? 2 : (v == 1 ? 1 : 0)); }
+    if (const char *s = getenv("BGD_LDSM_STRIPS")) { const int v = atoi(s); t.ldsm_strips = v >= 2 ? 2 : (v == 1 ? 1 : 0); }
     if (const char *s = getenv("BGD_LDSM_STAGES")) t.ldsm_stages = std::max(0, std::min(8, atoi(s)));
     if (const char *s = getenv("BGD_LDSM_BLOCKS")) t.ldsm_blocks = std::max(0, atoi(s));
     if (const char *s = getenv("BGD_COL_THREADS_C2")) t.threads_c2 = atoi(s) >= 256 ? 256 : 128;
@@ -45,8 +45,8 @@ Tuning read_tuning()
 
 bool classify(int T, const Tuning &tn, bool use_ldsm, Key *k)
 {
-    if (use_ldsm && T <= 32 * ldsm::kMaxNW) {
-        *k = Key{0, (T + 31) / 32, (T & 1) == 0};
+    if (use_ldsm && T <= 16 * ldsm::kMaxNH) {
+        *k = Key{0, (T + 15) / 16, (T & 1) == 0};
         return true;
     }
     int C = T <= tn.t_c4 ? 4 : (T <= tn.t_c2 ? 2 : 1);
@@ -172,10 +172,10 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
             lprm.vid_T = d_T + pos;
             lprm.vid_out = d_outi + pos;
             lprm.N = N;
-            // long odd videos run close to the HBM limit and gain from wider rows per copy (+8 % at T = 181);
+            // odd videos of more than 160 frames run close to the HBM limit and gain from wider rows per copy (+8 % at T = 181);
             // even T (bound by the LOP3 pipe) and short videos gain from the finer-grained CTAs (+3..6 %)
             // (profiles/r1_sweep_ldsm_strips.txt)
-            lprm.strips = tn.ldsm_strips > 0 ? tn.ldsm_strips : ((!key.even && key.NW >= 5) ? 2 : 1);
+            lprm.strips = tn.ldsm_strips > 0 ? tn.ldsm_strips : ((!key.even && key.NW >= 11) ? 2 : 1);
             const int tile_w = lprm.strips * ldsm::kStripW;
             lprm.tiles_per_video = (int32_t)((N + tile_w - 1) / tile_w);
             lprm.num_tiles = nv * lprm.tiles_per_video;
@@ -183,12 +183,12 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
                 rc = fail(BGD_ERR_UNSUPPORTED, "median (ldsm): %lld tiles in one call; split the batch", (long long)lprm.num_tiles);
                 break;
             }
-            lprm.rows_cap = key.NW * 32;
+            lprm.rows_cap = key.NW * 16;
             lprm.one = 1u;
             // buffers + mbarriers + slack to align the buffers to the 1024-byte swizzle atom; as many stages as
             // fit beside the CTA count the registers allow (1 KB per CTA is reserved by the driver)
             const size_t tile_bytes = (size_t)lprm.rows_cap * tile_w;
-            const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks : (key.NW <= 6 ? 8 : 6) / lprm.strips;
+            const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks : (key.NW <= 12 ? 8 : 6) / lprm.strips;
             const size_t per_block = (size_t)dp.smem_per_sm / blocks - 1024;
             int stages = tn.ldsm_stages > 0 ? tn.ldsm_stages : (int)((per_block - 1024 - 64) / tile_bytes);
             stages = std::max(1, std::min(stages, tn.ldsm_stages > 0 ? 8 : 4));

@@ -20,8 +20,10 @@
 // (g = lane / 4, q = lane % 4) owns byte columns 16 chunk(q) + g and + 8 of it for ALL T rows,
 // chunk(q) = {0,4,1,5}[q] for the even warp and {2,6,3,7}[q] for the odd one.  One ldmatrix.x2
 // gives it 8 rows of both; 8 registers (32 rows) of a column are bit-transposed in place (3 stages of masked
-// shifts) into 8 plane words: word b holds bit b of 32 rows.  A column of T rows is NW =
-// ceil(T / 32) such groups.  Per pass b = 7..0 and word:  z = alive & plane_b (LOP3), POPC(z)
+// shifts) into 8 plane words: word b holds bit b of 32 rows.  A column of T rows is NH = ceil(T / 16)
+// half groups: NH / 2 full groups per column plus, when NH is odd, one group that the lane's two
+// columns share (16 rows each; the columns' alive masks keep them apart), so the work follows T in
+// steps of 16 rows.  Per pass b = 7..0 and word:  z = alive & plane_b (LOP3), POPC(z)
 // accumulated by IMAD (neither on the LOP3 pipe), and alive &= plane_b ^ keep (LOP3).  The rank
 // bookkeeping is 4 bitwise operations per column and pass.
 //  * Even T: the second rank (T/2) shares the first's state until the pass in which they
@@ -37,8 +39,8 @@ namespace bgd {
 namespace ldsm {
 
 constexpr int kStripW = 128;              // bytes per TMA strip (= the 128-byte swizzle span); 2 warps per strip
-constexpr int kMaxStrips = 4;             // a CTA tile is 1, 2 or 4 strips wide
-constexpr int kMaxNW = 8;                 // T <= 256
+constexpr int kMaxStrips = 2;             // a CTA tile is 1 or 2 strips wide
+constexpr int kMaxNH = 16;                // T <= 256: at most 16 half groups (of 16 rows) per column
 
 struct alignas(64) LParams {
     CUtensorMap maps[colplane::kNumMaps];  // maps[k]: frames as [rows][N] uint8, box 128 bytes x 2^k rows, SWIZZLE_128B
@@ -49,17 +51,18 @@ struct alignas(64) LParams {
     int64_t N;
     int64_t num_tiles;
     int32_t tiles_per_video;
-    int32_t rows_cap;            // smem rows per strip (= NW * 32)
+    int32_t rows_cap;            // smem rows per strip (= NH * 16)
     uint32_t one;                // 1, opaque to the compiler: keeps count accumulation on IMAD
-    int32_t strips;              // strips per CTA tile (1, 2 or 4): tile width = 128 * strips, block = 64 * strips threads
+    int32_t strips;              // strips per CTA tile (1 or 2): tile width = 128 * strips, block = 64 * strips threads
     int32_t stages;              // tile buffers per CTA (ring); tile i of a CTA lives in buffer i % stages
     int32_t max_blocks_per_sm;   // 0 = as many as fit
 };
 
-int launch(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);
-int launch_lo(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NW 1..4
-int launch_mid(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);  // NW 5..6
-int launch_hi(int NW, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NW 7..8
+int launch(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);
+int launch_q0(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 1..6
+int launch_q1(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 7..10
+int launch_q2(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 11..13
+int launch_q3(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 14..16
 
 #ifdef __CUDACC__
 using colplane::bit_transpose8;
@@ -103,12 +106,15 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-template <int NW, int STRIPS> constexpr int min_blocks() { return (NW <= 6 ? 8 : 6) / STRIPS; }
+template <int NH, int STRIPS> constexpr int min_blocks() { return (NH <= 12 ? 8 : 6) / STRIPS; }
 
-template <int NW, bool EVEN, int STRIPS>
-__global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
+template <int NH, bool EVEN, int STRIPS>
+__global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
 {
     constexpr int kTileW = STRIPS * kStripW;
+    constexpr int FW = NH / 2;                           // full 32-row groups per column
+    constexpr bool HALF = (NH & 1) != 0;                 // plus one group shared by the lane's two columns
+    constexpr int NWC = FW + (HALF ? 1 : 0);             // plane words a column's select walks
     extern __shared__ uint8_t smem_raw[];
     // the 128-byte swizzle pattern repeats every 1024 bytes of shared-memory address: align the tile to it
     uint8_t *buf = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -196,13 +202,20 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
 
         // ---- shared memory -> registers (transposing loads), then 8x8 bit transposes -----------
         // P[c][k][m] before the transpose: rows 32 k + 4 m .. + 3 of column c, one per byte
-        uint32_t P[2][NW][8];
+        // PS[m]: rows 32 FW + 4 m .. + 3 of column 0 (m < 4) / rows 32 FW + 4 (m - 4) .. + 3 of column 1 (m >= 4)
+        uint32_t P[2][FW > 0 ? FW : 1][8], PS[8];
 #pragma unroll
-        for (int k = 0; k < NW; ++k) {
+        for (int k = 0; k < FW; ++k) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 ldsm_x2_trans_b8(P[0][k][2 * j], P[1][k][2 * j], P[0][k][2 * j + 1], P[1][k][2 * j + 1],
                                  ld_slot + (uint32_t)((k * 32 + j * 8) * kStripW));
+        }
+        if (HALF) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                ldsm_x2_trans_b8(PS[2 * j], PS[4 + 2 * j], PS[2 * j + 1], PS[4 + 2 * j + 1],
+                                 ld_slot + (uint32_t)((FW * 32 + j * 8) * kStripW));
         }
         __syncthreads();                                 // every lane has its columns: buffer is free
         {
@@ -214,19 +227,21 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
             slot = slot + 1 == stages ? 0 : slot + 1;
         }
 #pragma unroll
-        for (int k = 0; k < NW; ++k) {
+        for (int k = 0; k < FW; ++k) {
             bit_transpose8(P[0][k]);
             bit_transpose8(P[1][k]);
         }
+        if (HALF) bit_transpose8(PS);
 
-        // ---- alive mask of the last word: bit 8 y + m is row 32 (NW-1) + 4 m + y --------------------
+        // ---- alive mask of a column's last word: bit 8 y + m is row 32 (NWC-1) + 4 m + y; in the shared
+        //      group column 0 owns bits m < 4 of every byte and column 1 (mask << 4) the bits m >= 4 -------
         uint32_t last_mask = 0u;
         {
-            const int n = T - 32 * (NW - 1);
+            const int n = T - 32 * (NWC - 1);
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 int cnt = (n - y + 3) >> 2;
-                cnt = cnt < 0 ? 0 : (cnt > 8 ? 8 : cnt);
+                cnt = cnt < 0 ? 0 : (cnt > (HALF ? 4 : 8) ? (HALF ? 4 : 8) : cnt);
                 last_mask |= ((1u << cnt) - 1u) << (8 * y);
             }
         }
@@ -235,10 +250,11 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
         int med[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            uint32_t alive[NW], alive2[EVEN ? NW : 1];
+            auto plane = [&](int k, int b) -> uint32_t { return (HALF && k == FW) ? PS[b] : P[c][k < FW ? k : 0][b]; };
+            uint32_t alive[NWC], alive2[EVEN ? NWC : 1];
 #pragma unroll
-            for (int k = 0; k < NW; ++k) {
-                alive[k] = k == NW - 1 ? last_mask : 0xFFFFFFFFu;
+            for (int k = 0; k < NWC; ++k) {
+                alive[k] = k == NWC - 1 ? (HALF ? last_mask << (4 * c) : last_mask) : 0xFFFFFFFFu;
                 if (EVEN) alive2[k] = alive[k];
             }
             int rank = (T - 1) >> 1;                     // 0-based rank of the lower middle among the alive rows
@@ -249,18 +265,18 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
             for (int b = 7; b >= 0; --b) {
                 int d = rc;                              // becomes rank - zeros
 #pragma unroll
-                for (int k = 0; k < NW; ++k) d = popc_acc(alive[k] & P[c][k][b], d, one);
+                for (int k = 0; k < NWC; ++k) d = popc_acc(alive[k] & plane(k, b), d, one);
                 uint32_t any0 = 0u;                      // rows of the upper middle's set whose bit is 0
                 if (EVEN) {
 #pragma unroll
-                    for (int k = 0; k < NW; ++k) any0 |= alive2[k] & ~P[c][k][b];
+                    for (int k = 0; k < NWC; ++k) any0 |= alive2[k] & ~plane(k, b);
                 }
                 const int m0 = d >> 31;                  // all-ones: rank < zeros, the bit is 0
                 rank = isel(rank, d, m0);
                 rc = isel(d, rc, m0);
                 lo |= ~m0 & (1 << b);
 #pragma unroll
-                for (int k = 0; k < NW; ++k) alive[k] &= P[c][k][b] ^ (uint32_t)m0;
+                for (int k = 0; k < NWC; ++k) alive[k] &= plane(k, b) ^ (uint32_t)m0;
                 if (EVEN) {
                     // shared state: the upper middle has rank + 1, its bit is 0 iff d + 1 < 0; own state: iff any0
                     const int m0_shared = (d + 1) >> 31;
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
                     diverged |= m2 ^ m0;
                     hi |= ~m2 & (1 << b);
 #pragma unroll
-                    for (int k = 0; k < NW; ++k) alive2[k] &= P[c][k][b] ^ (uint32_t)m2;
+                    for (int k = 0; k < NWC; ++k) alive2[k] &= plane(k, b) ^ (uint32_t)m2;
                 }
             }
             med[c] = EVEN ? ((lo + hi) >> 1) : lo;
@@ -283,17 +299,17 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NW, STRIPS>()) median_
     }
 }
 
-template <int NW, bool EVEN, int STRIPS>
+template <int NH, bool EVEN, int STRIPS>
 int launch_strips(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
 {
     constexpr int kThreads = 64 * STRIPS;
-    auto kern = median_ldsm_kernel<NW, EVEN, STRIPS>;
+    auto kern = median_ldsm_kernel<NH, EVEN, STRIPS>;
     BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int blocks_per_sm = 0;
     BGD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
     if (blocks_per_sm < 1)
-        return fail(BGD_ERR_CUDA, "median (ldsm): kernel NW=%d does not fit an SM (%zu B smem)", NW, smem);
+        return fail(BGD_ERR_CUDA, "median (ldsm): kernel NH=%d does not fit an SM (%zu B smem)", NH, smem);
     if (prm.max_blocks_per_sm > 0 && blocks_per_sm > prm.max_blocks_per_sm) blocks_per_sm = prm.max_blocks_per_sm;
     const int64_t cap = (int64_t)sm_count * blocks_per_sm;
     const int grid = (int)(prm.num_tiles < cap ? prm.num_tiles : cap);
@@ -303,18 +319,17 @@ int launch_strips(const LParams &prm, int sm_count, size_t smem, cudaStream_t st
     return BGD_OK;
 }
 
-template <int NW, bool EVEN>
+template <int NH, bool EVEN>
 int launch_one(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
 {
-    return prm.strips == 4 ? launch_strips<NW, EVEN, 4>(prm, sm_count, smem, stream)
-           : prm.strips == 2 ? launch_strips<NW, EVEN, 2>(prm, sm_count, smem, stream)
-                             : launch_strips<NW, EVEN, 1>(prm, sm_count, smem, stream);
+    return prm.strips == 2 ? launch_strips<NH, EVEN, 2>(prm, sm_count, smem, stream)
+                           : launch_strips<NH, EVEN, 1>(prm, sm_count, smem, stream);
 }
 
-template <int NW>
+template <int NH>
 int launch_parity(bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
 {
-    return even ? launch_one<NW, true>(prm, sm_count, smem, stream) : launch_one<NW, false>(prm, sm_count, smem, stream);
+    return even ? launch_one<NH, true>(prm, sm_count, smem, stream) : launch_one<NH, false>(prm, sm_count, smem, stream);
 }
 #endif  // __CUDACC__
 
