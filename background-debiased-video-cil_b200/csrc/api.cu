@@ -136,7 +136,7 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
         return fail(BGD_ERR_UNSUPPORTED,
                     "median: the TMA variants need N %% 16 == 0, 16-byte aligned buffers and at most ~500 frames per video (T=%lld N=%lld)",
                     (long long)T_max, (long long)N);
-    // AUTO / LDSM: videos of up to 256 frames take the transposing-load kernel, longer ones the column-plane kernel
+    // AUTO / LDSM: videos of up to 512 frames take the transposing-load kernel, longer ones the column-plane kernel
     if (variant == BGD_MEDIAN_COLPLANE || variant == BGD_MEDIAN_LDSM || (variant == BGD_MEDIAN_AUTO && can_col))
         return median_colplane_varlen(d_frames, h_offsets, V, N, d_out, variant != BGD_MEDIAN_COLPLANE, stream);
     if (variant == BGD_MEDIAN_BITSLICED || (variant == BGD_MEDIAN_AUTO && can_bit))

@@ -49,6 +49,10 @@ bool classify(int T, const Tuning &tn, bool use_ldsm, Key *k)
         *k = Key{0, (T + 15) / 16, (T & 1) == 0};
         return true;
     }
+    if (use_ldsm && T <= 512) {                       // one column per lane: whole 32-row groups
+        *k = Key{0, 2 * ((T + 31) / 32), (T & 1) == 0};
+        return true;
+    }
     int C = T <= tn.t_c4 ? 4 : (T <= tn.t_c2 ? 2 : 1);
     for (; C >= 1; C /= 2) {
         const int rpw = 32 / C;
@@ -176,6 +180,7 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
             // even T (bound by the LOP3 pipe) and short videos gain from the finer-grained CTAs (+3..6 %)
             // (profiles/r1_sweep_ldsm_strips.txt)
             lprm.strips = tn.ldsm_strips > 0 ? tn.ldsm_strips : ((!key.even && key.NW >= 11) ? 2 : 1);
+            if (key.NW > ldsm::kMaxNH) lprm.strips = 1;   // one-column mode is instantiated for one strip
             const int tile_w = lprm.strips * ldsm::kStripW;
             lprm.tiles_per_video = (int32_t)((N + tile_w - 1) / tile_w);
             lprm.num_tiles = nv * lprm.tiles_per_video;
@@ -188,7 +193,8 @@ int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, in
             // buffers + mbarriers + slack to align the buffers to the 1024-byte swizzle atom; as many stages as
             // fit beside the CTA count the registers allow (1 KB per CTA is reserved by the driver)
             const size_t tile_bytes = (size_t)lprm.rows_cap * tile_w;
-            const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks : (key.NW <= 12 ? 8 : 6) / lprm.strips;
+            const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks
+                               : (key.NW <= 12 ? 8 : (key.NW <= ldsm::kMaxNH ? 6 : (key.NW <= 24 ? 3 : 2))) / lprm.strips;
             const size_t per_block = (size_t)dp.smem_per_sm / blocks - 1024;
             int stages = tn.ldsm_stages > 0 ? tn.ldsm_stages : (int)((per_block - 1024 - 64) / tile_bytes);
             stages = std::max(1, std::min(stages, tn.ldsm_stages > 0 ? 8 : 4));

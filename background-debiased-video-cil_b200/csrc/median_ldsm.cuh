@@ -1,4 +1,4 @@
-// Temporal median, transposing-load bit-plane select (BGD_MEDIAN_LDSM) -- the AUTO path for T <= 256.
+// Temporal median, transposing-load bit-plane select (BGD_MEDIAN_LDSM) -- the AUTO path for T <= 512.
 //
 // Replaces  np.median(frames, axis=0).astype(np.uint8)   (cil_tools/extract_background.py:73,
 // libs/loader/comix_loader.py:161); bit-exact:  out[n] = (s[(T-1)/2] + s[T/2]) >> 1.
@@ -63,6 +63,8 @@ int launch_q0(int NH, bool even, const LParams &prm, int sm_count, size_t smem, 
 int launch_q1(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 7..10
 int launch_q2(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 11..13
 int launch_q3(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 14..16
+int launch_q4(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 18..24 (one column per lane)
+int launch_q5(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);   // NH 26..32 (one column per lane)
 
 #ifdef __CUDACC__
 using colplane::bit_transpose8;
@@ -106,11 +108,21 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-template <int NH, int STRIPS> constexpr int min_blocks() { return (NH <= 12 ? 8 : 6) / STRIPS; }
+// NH <= 16 (T <= 256): a lane keeps both byte columns its ldmatrix fragments carry (COLS = 2, 2 warps per
+// strip).  NH = 18, 20, .. 32 (256 < T <= 512): 8 .. 16 full groups of one column are all the registers
+// hold, so twice the warps read the strip and each keeps one of the two columns (COLS = 1).
+template <int NH> __host__ __device__ constexpr int cols_of() { return NH <= kMaxNH ? 2 : 1; }
+template <int NH, int STRIPS> __host__ __device__ constexpr int threads_of() { return 64 * STRIPS * (3 - cols_of<NH>()); }
+template <int NH, int STRIPS> __host__ __device__ constexpr int min_blocks()
+{
+    return NH <= 12 ? 8 / STRIPS : (NH <= kMaxNH ? 6 / STRIPS : (NH <= 24 ? 3 : 2) / STRIPS);
+}
 
 template <int NH, bool EVEN, int STRIPS>
-__global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
+__global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIPS>()) median_ldsm_kernel(const __grid_constant__ LParams prm)
 {
+    constexpr int COLS = cols_of<NH>();
+    static_assert(COLS == 2 || (NH % 2 == 0 && NH <= 32), "one-column mode takes whole 32-row groups, T <= 512");
     constexpr int kTileW = STRIPS * kStripW;
     constexpr int FW = NH / 2;                           // full 32-row groups per column
     constexpr bool HALF = (NH & 1) != 0;                 // plus one group shared by the lane's two columns
@@ -129,10 +141,12 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_
     // ldmatrix address role: lane supplies row r8 = 4 * (lane / 16) + lane % 4 (mod 8) of the 16-byte
     // chunk quarter (lane % 16) / 4 reads; chunk c of row r sits at 16 * (c ^ (r % 8))
     const int r8 = ((lane >> 4) << 2) | (lane & 3);
-    const uint32_t ld_base = smem_u32(buf) + (uint32_t)(warp >> 1) * strip_bytes +
+    const int strip_id = COLS == 2 ? warp >> 1 : warp >> 2;
+    const bool second = COLS == 1 && ((warp >> 1) & 1);  // one-column mode: this warp keeps the fragments' second column
+    const uint32_t ld_base = smem_u32(buf) + (uint32_t)strip_id * strip_bytes +
                              (uint32_t)(r8 * kStripW + ((chunk_of((lane & 15) >> 2) ^ r8) << 4));
     // data role: columns of the tile owned by this lane
-    const int colA = (warp >> 1) * kStripW + chunk_of(lane & 3) * 16 + (lane >> 2), colB = colA + 8;
+    const int colA = strip_id * kStripW + chunk_of(lane & 3) * 16 + (lane >> 2) + (second ? 8 : 0), colB = colA + 8;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(bar + s, 1);
@@ -203,13 +217,21 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_
         // ---- shared memory -> registers (transposing loads), then 8x8 bit transposes -----------
         // P[c][k][m] before the transpose: rows 32 k + 4 m .. + 3 of column c, one per byte
         // PS[m]: rows 32 FW + 4 m .. + 3 of column 0 (m < 4) / rows 32 FW + 4 (m - 4) .. + 3 of column 1 (m >= 4)
-        uint32_t P[2][FW > 0 ? FW : 1][8], PS[8];
+        uint32_t P[COLS][FW > 0 ? FW : 1][8], PS[8];
 #pragma unroll
         for (int k = 0; k < FW; ++k) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                ldsm_x2_trans_b8(P[0][k][2 * j], P[1][k][2 * j], P[0][k][2 * j + 1], P[1][k][2 * j + 1],
-                                 ld_slot + (uint32_t)((k * 32 + j * 8) * kStripW));
+            for (int j = 0; j < 4; ++j) {
+                if constexpr (COLS == 2) {
+                    ldsm_x2_trans_b8(P[0][k][2 * j], P[1][k][2 * j], P[0][k][2 * j + 1], P[1][k][2 * j + 1],
+                                     ld_slot + (uint32_t)((k * 32 + j * 8) * kStripW));
+                } else {
+                    uint32_t a0, b0, a1, b1;
+                    ldsm_x2_trans_b8(a0, b0, a1, b1, ld_slot + (uint32_t)((k * 32 + j * 8) * kStripW));
+                    P[0][k][2 * j] = second ? b0 : a0;
+                    P[0][k][2 * j + 1] = second ? b1 : a1;
+                }
+            }
         }
         if (HALF) {
 #pragma unroll
@@ -228,8 +250,8 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_
         }
 #pragma unroll
         for (int k = 0; k < FW; ++k) {
-            bit_transpose8(P[0][k]);
-            bit_transpose8(P[1][k]);
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) bit_transpose8(P[c][k]);
         }
         if (HALF) bit_transpose8(PS);
 
@@ -247,9 +269,9 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_
         }
 
         // ---- 8-pass MSB-first rank select, per column ------------------------------------------------
-        int med[2];
+        int med[2] = {0, 0};
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < COLS; ++c) {
             auto plane = [&](int k, int b) -> uint32_t { return (HALF && k == FW) ? PS[b] : P[c][k < FW ? k : 0][b]; };
             uint32_t alive[NWC], alive2[EVEN ? NWC : 1];
 #pragma unroll
@@ -295,14 +317,14 @@ __global__ void __launch_bounds__(64 * STRIPS, min_blocks<NH, STRIPS>()) median_
         const int64_t col0 = (int64_t)ct * kTileW;
         uint8_t *dst = prm.out + prm.vid_out[vid] * prm.N + col0;
         if (col0 + colA < prm.N) dst[colA] = (uint8_t)med[0];
-        if (col0 + colB < prm.N) dst[colB] = (uint8_t)med[1];
+        if (COLS == 2 && col0 + colB < prm.N) dst[colB] = (uint8_t)med[1];
     }
 }
 
 template <int NH, bool EVEN, int STRIPS>
 int launch_strips(const LParams &prm, int sm_count, size_t smem, cudaStream_t stream)
 {
-    constexpr int kThreads = 64 * STRIPS;
+    constexpr int kThreads = threads_of<NH, STRIPS>();
     auto kern = median_ldsm_kernel<NH, EVEN, STRIPS>;
     BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BGD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

@@ -22,7 +22,9 @@ int launch(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cud
     if (NH <= 6) return launch_q0(NH, even, prm, sm_count, smem, stream);
     if (NH <= 10) return launch_q1(NH, even, prm, sm_count, smem, stream);
     if (NH <= 13) return launch_q2(NH, even, prm, sm_count, smem, stream);
-    return launch_q3(NH, even, prm, sm_count, smem, stream);
+    if (NH <= 16) return launch_q3(NH, even, prm, sm_count, smem, stream);
+    if (NH <= 24) return launch_q4(NH, even, prm, sm_count, smem, stream);
+    return launch_q5(NH, even, prm, sm_count, smem, stream);
 }
 
 }  // namespace ldsm

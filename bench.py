@@ -40,6 +40,18 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner
+# to stdout under NCCL_DEBUG=VERSION), so keep a private handle on the real stdout for the JSON line and
+# point file descriptor 1 at stderr for everything else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -155,7 +167,7 @@ def run_reference(args):
         f_all += frames
     value = f_all / t_all
     sample = f"{procs} videos per step (one per process), T~U[120,240], 240x320x3, np.median only (no decode)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "bg_extraction_frames_per_sec", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -164,7 +176,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def run_ours(args):
@@ -346,7 +358,7 @@ def run_ours(args):
                 traffic = ratio * step_bytes
             except Exception:
                 traffic = None
-        print(json.dumps({
+        emit({
             "metric": "bg_extraction_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -364,7 +376,7 @@ def run_ours(args):
             "clocks": clk.summary(),
             "parity_spotcheck": ok,
             "bgmix": bgmix,
-        }))
+        })
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -47,9 +47,9 @@ typedef enum bgd_status {
 #define BGD_MEDIAN_AUTO      0
 #define BGD_MEDIAN_SWAR      1   /* thread-per-4-columns byte-SIMD binary search; any T, any N */
 #define BGD_MEDIAN_BITSLICED 2   /* TMA-staged cooperative bit-sliced select; needs N % 16 == 0 */
-#define BGD_MEDIAN_COLPLANE  3   /* TMA-staged thread-per-column bit-plane select (AUTO's choice for T > 256) */
+#define BGD_MEDIAN_COLPLANE  3   /* TMA-staged thread-per-column bit-plane select (AUTO's choice for 512 < T <= 544) */
 #define BGD_MEDIAN_LDSM      4   /* TMA-staged, transposing shared-memory loads, POPC counting (AUTO's choice for
-                                    T <= 256; longer videos of the same call take COLPLANE) */
+                                    T <= 512; longer videos of the same call take COLPLANE) */
 
 /* ---- library / device ------------------------------------------------------------------ */
 
