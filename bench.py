@@ -287,6 +287,29 @@ def run_ours(args):
     e2e_value = world * rows_e * k_e2e / float(te.item())
     e2e_ok = bool(torch.equal(h_out.to(dev), out[:Ve]))
 
+    # ---- the path's one collective: all-gather of the background index + pixels for the mix pool
+    #      (pool.BackgroundPool.all_gather).  Outside `value`; reported beside it.
+    gather = None
+    if world > 1:
+        try:
+            from bgdebias_b200.pool import BackgroundPool
+            names = [f"r{rank}_v{i:05d}" for i in range(V)]
+            BackgroundPool.all_gather(names[:8], out[:8])                    # warm-up (NCCL channel set-up)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            all_names, all_bgs = BackgroundPool.all_gather(names, out)
+            g1.record()
+            barrier()
+            tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(all_bgs[rank * V:(rank + 1) * V], out)) and len(all_names) == world * V
+            gather = {"ms": float(tg.item()), "backgrounds": int(all_bgs.shape[0]), "bytes_per_rank_out": int(all_bgs.numel()),
+                      "GB/s_per_rank": all_bgs.numel() / (float(tg.item()) * 1e-3) / 1e9, "backend": "nccl", "parity": same}
+            del all_bgs
+        except Exception as e:
+            gather = {"error": repr(e)}
+
     # ---- BG-mix (configs[4]): 64 clips x 8 x 224 x 224 per step --------------------------------
     bgmix = None
     try:
@@ -376,6 +399,7 @@ def run_ours(args):
             "clocks": clk.summary(),
             "parity_spotcheck": ok,
             "bgmix": bgmix,
+            "pool_all_gather": gather,
         })
     if world > 1:
         dist.barrier()

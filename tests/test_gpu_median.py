@@ -214,3 +214,18 @@ def test_kernels_were_launched(bgd):
     before = cabi.kernel_launch_count()
     _gpu_median(ops, np.zeros((3, 32), np.uint8))
     assert cabi.kernel_launch_count() > before
+
+
+def test_one_call_mixes_every_kernel_family(bgd):
+    """One varlen call whose videos land in the two-column, shared-half-group and one-column
+    instantiations of the transposing-load kernel and in the column-plane kernel (T > 512)."""
+    ops, cabi = bgd
+    cabi.set_median_variant(0)
+    rng = np.random.default_rng(11)
+    N = 2048 + 48
+    Ts = [5, 16, 37, 64, 100, 181, 240, 300, 501, 530]
+    offs = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+    fr = rng.integers(0, 256, (int(offs[-1]), N), dtype=np.uint8)
+    out = torch.ops.bgdebias.temporal_median_varlen(torch.from_numpy(fr).cuda(), torch.from_numpy(offs)).cpu().numpy()
+    for v, T in enumerate(Ts):
+        np.testing.assert_array_equal(out[v], c_oracle.temporal_median(fr[offs[v]:offs[v + 1]]), err_msg=f"T={T}")
