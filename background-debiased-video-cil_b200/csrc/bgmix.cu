@@ -20,6 +20,10 @@ namespace bgd {
 namespace {
 
 constexpr int kThreads = 256;
+// 8 CTAs per SM (32 registers) and 4 frames of loads in flight per thread: the kernel waits on memory
+// (long-scoreboard stalls), so occupancy beats registers here (profiles/r1_bgmix_unroll_occupancy.txt)
+constexpr int kMixUnroll = 4;
+constexpr int kMixMinBlocks = 8;
 
 struct MixParams {
     const uint8_t *fg;
@@ -38,7 +42,7 @@ template <typename PoolT>
 __device__ __forceinline__ float load_bg(const PoolT *p) { return (float)__ldg(p); }
 
 template <typename PoolT, int PX>
-__global__ void __launch_bounds__(kThreads) bgmix_kernel(const MixParams prm)
+__global__ void __launch_bounds__(kThreads, kMixMinBlocks) bgmix_kernel(const MixParams prm)
 {
     __shared__ float s_lut[3 * 256];
     for (int i = threadIdx.x; i < 3 * 256; i += kThreads) s_lut[i] = __ldg(prm.lut + i);
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) bgmix_kernel(const MixParams prm)
     const uint8_t *fg = prm.fg + (b * prm.T * HW + p0) * 3;
     float *out = prm.out + b * prm.T * 3 * HW + p0;
 
-#pragma unroll 2
+#pragma unroll kMixUnroll
     for (int64_t t = 0; t < prm.T; ++t) {
         uint8_t px[3 * PX];
         if (PX == 4) {
