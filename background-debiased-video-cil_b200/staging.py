@@ -14,6 +14,8 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import ops as _ops  # noqa: F401  (registers torch.ops.bgdebias.*)
+
 
 class _Slab:
     def __init__(self, nbytes: int, device: torch.device):
