@@ -56,3 +56,32 @@ def test_cli_folder_of_videos(tmp_path, workers):
     marker.write_bytes(b"kept")
     eb.main(argv)
     assert marker.read_bytes() == b"kept"
+
+
+def test_per_video_functions_keep_the_reference_signatures(tmp_path):
+    """extract_background.bg_extraction_tmf(data_path, dest, from_video, interval, max_frames, avg_method)
+    (reference :42-43,108) and comix_loader.bg_extraction_tmf(data_path, dest) (reference
+    comix_loader.py:148-164): same return value (the uint8 median frame) and the JPEG on disk."""
+    from bgdebias_b200 import comix_loader as cl, extract_background as eb
+    rng = np.random.default_rng(9)
+    fr = rng.integers(0, 256, (23, H, W, 3), dtype=np.uint8)
+    _write(tmp_path / "v.avi", fr)
+    out = eb.bg_extraction_tmf(tmp_path / "v.avi", tmp_path / "v.jpg", True, 3, 5, 0)
+    kept = mo.select_frame_indices(23, 3, 5)
+    exp = mo.temporal_median_np([fr[i] for i in kept])
+    assert out.dtype == np.uint8 and np.array_equal(out, exp)
+    assert np.array_equal(cv2.imread(str(tmp_path / "v.jpg")), cv2.imdecode(cv2.imencode(".jpg", exp)[1], cv2.IMREAD_COLOR))
+
+    # raw-frame folder: every image of the folder, decoded by cv2.imread like the reference (:157-160)
+    folder = tmp_path / "frames"
+    folder.mkdir()
+    for i, f in enumerate(fr[:12]):
+        cv2.imwrite(str(folder / f"img_{i + 1:05d}.jpg"), f)
+    decoded = [cv2.imread(str(p)) for p in folder.glob("*")]
+    out2 = cl.bg_extraction_tmf(folder, tmp_path / "f.jpg")
+    assert np.array_equal(out2, mo.temporal_median_np(decoded))
+    assert (tmp_path / "f.jpg").exists()
+    with pytest.raises(NotImplementedError):
+        cl.bg_extraction_tmf(folder, tmp_path / "g.jpg", from_video=True)
+    with pytest.raises(NotImplementedError):
+        eb.sim_cam_motion_bg_extract(tmp_path / "v.avi", tmp_path / "s.jpg", True, 1, 10, 0)
