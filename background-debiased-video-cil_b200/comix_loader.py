@@ -31,7 +31,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .pool import BackgroundPool, resize_like_reference, resized_hw
+from .pool import BackgroundPool, BackgroundStore, resize_like_reference, resized_hw
 
 try:  # mmaction is optional: register into its registries when it is importable
     from mmaction.datasets import RawframeDataset as _MMRawframeDataset
@@ -194,6 +194,7 @@ class BackgroundMixDataset(_Base):
         self._bg_reader = bg_reader
         self._pool: Optional[BackgroundPool] = None
         self._pool_key = None
+        self._store: Optional[BackgroundStore] = None
         self._resized_cache = {}
 
         # pool assembly: the three modes of comix_loader.py:84-103
@@ -234,13 +235,17 @@ class BackgroundMixDataset(_Base):
         return self._read_bg(path).float(), -2      # to pass sanity check
 
     def device_pool(self) -> BackgroundPool:
-        """The pool decoded + resized once and kept on ``self.device``; rebuilt when ``bg_files`` was
-        replaced or mutated by the caller (the CIL trainer does that between tasks,
-        libs/cil/cil.py:150-160,193-195,390-393)."""
+        """The pool for the current ``bg_files``, index i = ``bg_files[i]``.  Every path is decoded + resized
+        once per dataset object and stays on ``self.device`` (:class:`BackgroundStore`); when the caller
+        replaces or mutates ``bg_files`` -- the CIL trainer does between tasks (libs/cil/cil.py:150-160,
+        193-195,390-393: unions and extensions of path lists) -- only paths not seen before are decoded and
+        the new pool is a new slot table over the same pixels."""
         key = tuple(self.bg_files)
         if self._pool is None or key != self._pool_key:
-            imgs = [self._read_bg(f) for f in self.bg_files]
-            self._pool = BackgroundPool.from_images(imgs, list(self.bg_files), self.bg_resize, self.device)
+            if self._store is None:
+                self._store = BackgroundStore(self.bg_resize, self.device)
+            self._store.ensure(self.bg_files, self._read_bg)
+            self._pool = self._store.view(list(self.bg_files))
             self._pool_key = key
         return self._pool
 
@@ -302,6 +307,8 @@ class BackgroundMixDataset(_Base):
         """Size of pool images after Resize, without touching the GPU (needs one image header)."""
         if self._pool is not None and tuple(self.bg_files) == self._pool_key:
             return self._pool.hw
+        if self._store is not None and len(self._store):
+            return self._store.hw                      # one shape per store
         key = self.bg_files[0] if self.bg_files else None
         if key not in self._resized_cache:
             img = self._read_bg(key)
@@ -323,7 +330,7 @@ class BackgroundMixDataset(_Base):
         lut = self._lut(tuple(mean), tuple(std))
         as_dev = lambda v, dt: torch.as_tensor(v, dtype=dt).to(dev, non_blocking=True)   # noqa: E731
         return torch.ops.bgdebias.bgmix_blend(
-            fg_u8.to(dev, non_blocking=True), pool.tensor, as_dev(bg_idx, torch.int32).clamp_(min=0),
+            fg_u8.to(dev, non_blocking=True), pool.tensor, pool.rows(as_dev(bg_idx, torch.int32).clamp_(min=0)),
             as_dev(bg_top, torch.int32), as_dev(bg_left, torch.int32), as_dev(bg_apply, torch.uint8), lut,
             torch.tensor(self.bg_mean), torch.tensor(self.bg_std), float(self.alpha), layout)
 

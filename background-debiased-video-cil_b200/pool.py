@@ -45,13 +45,21 @@ class BackgroundPool:
             raise ValueError("one name per pool slot")
         self.tensor = tensor
         self.names: List[str] = list(names)
+        self.index_names: List[str] = self.names          # pool index i -> name (differs from `names` for a store view)
+        self.slots: Optional[torch.Tensor] = None         # int32 [len(index_names)]: pool index -> row of `tensor`; None = identity
 
     def __len__(self) -> int:
-        return self.tensor.shape[0]
+        return len(self.index_names)
 
     @property
     def hw(self) -> tuple:
         return int(self.tensor.shape[2]), int(self.tensor.shape[3])
+
+    def rows(self, bg_idx: torch.Tensor) -> torch.Tensor:
+        """Rows of ``tensor`` for pool indices ``bg_idx`` (int32, on the pool's device)."""
+        if self.slots is None:
+            return bg_idx
+        return self.slots[bg_idx.clamp(min=0, max=len(self.index_names) - 1).long()]
 
     @classmethod
     def from_images(cls, images: Sequence, names: Optional[Sequence[str]] = None, bg_resize: Optional[int] = 256,
@@ -107,3 +115,75 @@ class BackgroundPool:
         parts = [gathered[r, : counts[r]] for r in range(world)]
         names = [n for per in names_per_rank for n in per]
         return names, torch.cat(parts, 0) if parts else gathered.view((0,) + item_shape)
+
+
+class BackgroundStore:
+    """Backgrounds resident on one device across pool changes.
+
+    The reference's trainer rewrites ``dataset.bg_files`` between CIL tasks -- ``keep_all_backgrounds``
+    (libs/cil/cil.py:193-195,690-694), ``cbf_full_bg`` (:146-160) and ``merge_bg_files`` (:390-393) are
+    unions / extensions of path lists -- and every sample then decodes its background again.  Here each
+    path is decoded + resized once, the pixels stay in one ``[capacity, 3, Hb, Wb]`` tensor, and a pool is
+    an int32 slot table over it: set operations on the path lists never copy or re-decode pixels, and
+    duplicates in ``bg_files`` (``extend`` creates them) share a slot and keep their draw probability.
+    """
+
+    def __init__(self, bg_resize: Optional[int] = 256, device="cuda", keep_uint8: bool = False):
+        self.bg_resize = bg_resize
+        self.device = torch.device(device)
+        self.keep_uint8 = keep_uint8
+        self.tensor: Optional[torch.Tensor] = None        # [capacity, 3, Hb, Wb]
+        self.slot_of: dict = {}                           # name -> slot
+        self.decoded = 0                                  # images decoded so far (what a rebuild would repeat)
+
+    def __len__(self) -> int:
+        return len(self.slot_of)
+
+    @property
+    def hw(self) -> tuple:
+        if self.tensor is None:
+            raise ValueError("empty background store")
+        return int(self.tensor.shape[2]), int(self.tensor.shape[3])
+
+    def ensure(self, names: Sequence[str], reader) -> None:
+        """Make every name resident; ``reader(name) -> uint8 [3, h, w]`` is called for new names only."""
+        new = [n for n in dict.fromkeys(names) if n not in self.slot_of]
+        if not new:
+            return
+        imgs = []
+        for n in new:
+            t = torch.as_tensor(reader(n))
+            if t.dim() != 3 or t.shape[0] != 3:
+                raise ValueError("background images must be [3, h, w]")
+            imgs.append(t.to(torch.uint8) if (self.keep_uint8 and self.bg_resize is None)
+                        else resize_like_reference(t, self.bg_resize))
+        shapes = {tuple(t.shape) for t in imgs}
+        if self.tensor is not None:
+            shapes.add(tuple(self.tensor.shape[1:]))
+        if len(shapes) != 1:
+            raise ValueError(f"backgrounds resize to different shapes {sorted(shapes)}; build one pool per shape")
+        used = len(self.slot_of)
+        need = used + len(imgs)
+        if self.tensor is None or need > self.tensor.shape[0]:
+            cap = max(need, 2 * (self.tensor.shape[0] if self.tensor is not None else 0))
+            grown = torch.empty((cap,) + tuple(imgs[0].shape), dtype=imgs[0].dtype, device=self.device)
+            if self.tensor is not None and used:
+                grown[:used].copy_(self.tensor[:used])
+            self.tensor = grown
+        self.tensor[used:need].copy_(torch.stack(imgs), non_blocking=True)
+        for i, n in enumerate(new):
+            self.slot_of[n] = used + i
+        self.decoded += len(new)
+
+    def view(self, names: Sequence[str]) -> "BackgroundPool":
+        """The pool whose index ``i`` is ``names[i]`` (the reference's ``bg_idx``): shares this store's
+        pixels; ``slots`` maps pool index -> row of ``tensor``."""
+        if len(names) == 0:
+            raise ValueError("empty background pool")
+        missing = [n for n in names if n not in self.slot_of]
+        if missing:
+            raise KeyError(f"{len(missing)} backgrounds are not resident (first: {missing[0]}); call ensure() first")
+        pool = BackgroundPool(self.tensor[:len(self.slot_of)], list(self.slot_of))
+        pool.index_names = list(names)
+        pool.slots = torch.tensor([self.slot_of[n] for n in names], dtype=torch.int32, device=self.device)
+        return pool

@@ -276,3 +276,59 @@ def test_host_entry_point_and_errors(env):
                                        torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
                                        torch.zeros(1, dtype=torch.int32, device=dev), torch.ones(1, dtype=torch.uint8, device=dev),
                                        d_lut, torch.tensor(bo.DEFAULT_MEAN), torch.tensor(bo.DEFAULT_STD), 0.5, "NHWC")
+
+
+def test_pool_lifecycle_across_tasks(env):
+    """The trainer's rewrites of ``dataset.bg_files`` between CIL tasks -- keep_all_backgrounds
+    (libs/cil/cil.py:193-195: ``_all_bg_files.update(bg_files); bg_files = list(_all_bg_files)``), cbf_full_bg
+    (:156-160: union of two lists) and merge_bg_files (:390-393: ``bg_files.extend(other.bg_files)``, duplicates
+    included) -- decode only the paths not seen before and blend exactly like a pool built from scratch."""
+    ops, cabi, cl, pool_mod = env
+    rng = np.random.default_rng(8)
+    T, H, W, B = 2, 32, 32, 12
+    fg = rng.integers(0, 256, (B, T, H, W, 3), dtype=np.uint8)
+    imgs = {f"/bg/v{i:02d}.jpg": rng.integers(0, 256, (3, 36, 48), dtype=np.uint8) for i in range(10)}
+    paths = sorted(imgs)
+    calls = []
+
+    def reader(p):
+        calls.append(p)
+        return imgs[p]
+
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        infos = [dict(frame_dir=f"/x/v{i:02d}", total_frames=T, label=i, sample=i) for i in range(B)]
+        pipeline = lambda info: dict(imgs=torch.from_numpy(fg[info["sample"]]), label=torch.tensor([0]), randAug=False)
+        ds = cl.BackgroundMixDataset(infos, pipeline, bg_dir=tmp, bg_resize=40, bg_crop_size=(H, W), with_randAug=True,
+                                     device_mix=True, bg_reader=reader, extract_bg_if_not_found=False)
+
+        def run(bg_files, seed):
+            ds.bg_files = bg_files
+            torch.manual_seed(seed)
+            samples = [ds.prepare_train_frames(i) for i in range(B)]
+            got = ds.gpu_collate(samples)["imgs"].cpu().numpy()
+            resized = np.stack([bo.bg_resize(imgs[p], 40).numpy() for p in bg_files])
+            exp = bo.mix_batch(fg, resized, [s["bg_idx"] for s in samples], [s["bg_top"] for s in samples],
+                               [s["bg_left"] for s in samples], [1] * B, crop=(H, W))
+            _assert_same(got, exp)
+            assert all(0 <= s["bg_idx"] < len(bg_files) for s in samples)
+
+        task0 = paths[:4]
+        run(list(task0), 1)
+        assert set(calls) == set(task0) and ds._store.decoded == 4
+        probes = len(calls) - 4                                          # the size probe of _pool_hw, before the pool exists
+        assert probes <= 1
+        # task 1 with keep_all_backgrounds: set union, arbitrary order
+        all_bg = set(task0)
+        all_bg.update(paths[3:7])
+        run(list(all_bg), 2)
+        assert set(calls) == set(paths[:7]) and len(calls) == 7 + probes  # v03 was not decoded again
+        # merge_bg_files: extend with an exemplar set's list (duplicates keep their draw probability)
+        merged = list(all_bg)
+        merged.extend(paths[5:9])
+        run(merged, 3)
+        assert len(calls) == 9 + probes
+        # cbf_full_bg: union of the train list and the merged exemplar list; nothing new to decode
+        run(list(set(task0) | set(merged)), 4)
+        assert len(calls) == 9 + probes
+        assert len(ds._store) == 9 and ds._store.decoded == 9

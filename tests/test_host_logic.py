@@ -145,3 +145,29 @@ def test_pool_all_gather_two_ranks():
         assert names == exp_names
         assert bgs.shape == (4, 4, 5, 3)
         assert [int(bgs[i, 0, 0, 0]) for i in range(4)] == [1, 2, 3, 2]
+
+
+def test_background_store_slots_without_gpu():
+    """BackgroundStore on the CPU device: names are decoded once, pools are slot tables over shared pixels."""
+    import numpy as np
+    import torch
+    from bgdebias_b200.pool import BackgroundStore
+    rng = np.random.default_rng(0)
+    imgs = {f"n{i}": torch.from_numpy(rng.integers(0, 256, (3, 8, 10), dtype=np.uint8)) for i in range(6)}
+    seen = []
+    store = BackgroundStore(bg_resize=None, device="cpu")
+    store.ensure(["n0", "n1", "n1"], lambda n: (seen.append(n), imgs[n])[1])
+    assert seen == ["n0", "n1"] and len(store) == 2
+    a = store.view(["n1", "n0", "n1"])
+    assert len(a) == 3 and a.slots.tolist() == [1, 0, 1] and a.hw == (8, 10)
+    store.ensure(["n1", "n4", "n2"], lambda n: (seen.append(n), imgs[n])[1])
+    assert seen == ["n0", "n1", "n4", "n2"] and store.decoded == 4
+    b = store.view(["n2", "n4", "n0"])
+    assert b.slots.tolist() == [3, 2, 0]
+    assert torch.equal(b.tensor[b.rows(torch.tensor([1]))[0]], imgs["n4"].float())
+    assert torch.equal(a.tensor[a.slots[0].item()], imgs["n1"].float())      # growth kept the old pixels
+    import pytest
+    with pytest.raises(KeyError):
+        store.view(["n5"])
+    with pytest.raises(ValueError):
+        store.ensure(["bad"], lambda n: torch.zeros(3, 9, 9, dtype=torch.uint8))
