@@ -413,6 +413,20 @@ int bgd_temporal_median_varlen_u8_host(const uint8_t *h_frames, const int64_t *h
     return median_host_pipeline(nullptr, h_frames, h_offsets, V, N, h_out, device);
 }
 
+int bgd_nan_temporal_reduce_f32(const float *d_frames, int64_t T, int64_t N, int avg_method, int zero_is_missing,
+                                uint8_t *d_out_u8, float *d_out_f32, void *stream)
+{
+    return launch_nan_reduce(d_frames, T, N, avg_method, zero_is_missing, d_out_u8, d_out_f32,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int bgd_nan_temporal_reduce_varlen_f32(const float *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, int avg_method,
+                                       int zero_is_missing, uint8_t *d_out_u8, float *d_out_f32, void *stream)
+{
+    return launch_nan_reduce_varlen(d_frames, h_offsets, V, N, avg_method, zero_is_missing, d_out_u8, d_out_f32,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 int bgd_bgmix_blend_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W, const float *d_bg_pool,
                         int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx, const int32_t *d_top,
                         const int32_t *d_left, const uint8_t *d_apply, const float *d_fg_lut, const float *h_bg_mean,

@@ -114,10 +114,43 @@ def bg_extraction_tmf(data_path: pathlib.Path, dest: pathlib.Path,
     return median_frame
 
 
-def sim_cam_motion_bg_extract(data_path, dest, from_video, interval, max_frames, avg_method):
-    """The reference's simulated-camera-motion variant (extract_background.py:78-99) is a float
-    NaN-masked median over random crops; it is outside this path's scope."""
-    raise NotImplementedError("--method sim_cam is not part of the B200 path; use the reference for it")
+SIM_CAM_CROP = 100
+
+
+def sim_cam_frames(data_path: pathlib.Path, interval: int, max_frames: int) -> torch.Tensor:
+    """The reference's loop (extract_background.py:81-92) up to the NaN marking: every ``interval``-th image
+    of the sorted folder except the last, at most ``max_frames``, each through ``RandomResizedCrop(size=100)``
+    on the host (torchvision itself: same torch-RNG draws, same antialiased resize).  float32 ``[T,100,100,3]``."""
+    from torchvision.io import read_image
+    from torchvision.transforms import Compose, RandomResizedCrop
+    cam_motion_pipeline = Compose([RandomResizedCrop(size=SIM_CAM_CROP)])
+    image_files = sorted(pathlib.Path(data_path).glob('*'))
+    out = []
+    for i, frame_f in enumerate(image_files[:-1:interval]):
+        if i == max_frames:
+            break
+        frame = read_image(str(frame_f)).float()
+        out.append(cam_motion_pipeline(frame).permute(1, 2, 0).contiguous())
+    if not out:
+        raise ValueError(f"no frames under {data_path}")       # reference: nanmedian of [] raises
+    return torch.stack(out)
+
+
+def sim_cam_background(data_path: pathlib.Path, interval: int, max_frames: int, avg_method: int, device=0) -> np.ndarray:
+    """uint8 ``[100,100,3]``: the ``ave_frame`` of extract_background.py:94-98.  Zeros count as missing
+    (:91); the NaN-masked median (``avg_method`` 0) or mean (1) over the frames runs on the GPU."""
+    from . import ops as _ops  # noqa: F401  (registers torch.ops.bgdebias.*)
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    frames = sim_cam_frames(data_path, interval, max_frames).to(dev)
+    return torch.ops.bgdebias.nan_temporal_reduce(frames, int(avg_method), True).cpu().numpy()
+
+
+def sim_cam_motion_bg_extract(data_path, dest, from_video, interval, max_frames, avg_method, device=0):
+    """Simulated-camera-motion extraction, same signature and side effect as the reference
+    (extract_background.py:78-99): reads the image folder ``data_path`` (``from_video`` is ignored there
+    too), writes ``dest`` and returns ``None``."""
+    ave_frame = sim_cam_background(pathlib.Path(data_path), interval, max_frames, avg_method, device)
+    cv2.imwrite(str(dest), cv2.cvtColor(ave_frame, cv2.COLOR_BGR2RGB))
 
 
 def bg_extract_multiple(paths: List[pathlib.Path], output_dir: pathlib.Path, from_video: bool,
@@ -128,9 +161,12 @@ def bg_extract_multiple(paths: List[pathlib.Path], output_dir: pathlib.Path, fro
     reduced many-per-launch; any other ``method`` callable is invoked video by video like the reference."""
     output_dir = pathlib.Path(output_dir)
     if method is not bg_extraction_tmf:
+        extra = {}
+        if method is sim_cam_motion_bg_extract:
+            extra['device'] = _shard.device_for(process_id, torch.cuda.device_count()) if device is None else device
         for data_path in paths:
             method(data_path, (output_dir / data_path.name).with_suffix('.jpg'), from_video, interval, max_frames,
-                   avg_method)
+                   avg_method, **extra)
         return []
     if device is None:
         device = _shard.device_for(process_id, torch.cuda.device_count())

@@ -84,6 +84,69 @@ def _(frames, offsets):
 
 
 # --------------------------------------------------------------------------- #
+# NaN-masked temporal median / mean (sim_cam extraction, extract_background.py:91-98)
+# --------------------------------------------------------------------------- #
+def _nan_reduce(frames: torch.Tensor, avg_method: int, zero_is_missing: bool, as_float: bool) -> torch.Tensor:
+    _require(frames.dtype == torch.float32, "nan_temporal_reduce: frames must be float32")
+    _require(frames.dim() >= 1 and frames.shape[0] > 0, "nan_temporal_reduce: frames must be [T, ...] with T > 0 "
+             "(the reference fails here too: nanmedian of nothing)")
+    _require(avg_method in (0, 1), "nan_temporal_reduce: avg_method must be 0 (median) or 1 (mean)")
+    frames = frames.contiguous()
+    out = torch.empty(frames.shape[1:], dtype=torch.float32 if as_float else torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _cabi.check(_cabi.lib().bgd_nan_temporal_reduce_f32(
+            frames.data_ptr(), frames.shape[0], out.numel(), int(avg_method), int(bool(zero_is_missing)),
+            None if as_float else out.data_ptr(), out.data_ptr() if as_float else None, _stream_ptr(frames.device)))
+    return out
+
+
+@torch.library.custom_op("bgdebias::nan_temporal_reduce", mutates_args=(), device_types="cuda")
+def nan_temporal_reduce(frames: torch.Tensor, avg_method: int, zero_is_missing: bool) -> torch.Tensor:
+    """uint8 ``[...]``: ``np.nanmedian`` / ``np.nanmean`` over axis 0, ``.astype(uint8)``."""
+    return _nan_reduce(frames, avg_method, zero_is_missing, False)
+
+
+@nan_temporal_reduce.register_fake
+def _(frames, avg_method, zero_is_missing):
+    return frames.new_empty(frames.shape[1:], dtype=torch.uint8)
+
+
+@torch.library.custom_op("bgdebias::nan_temporal_reduce_varlen", mutates_args=(), device_types="cuda")
+def nan_temporal_reduce_varlen(frames: torch.Tensor, offsets: torch.Tensor, avg_method: int, zero_is_missing: bool) -> torch.Tensor:
+    """V frame folders concatenated along T (``offsets`` [V+1], host or device int64) -> uint8 ``[V, ...]``."""
+    _require(frames.dtype == torch.float32 and frames.dim() >= 1, "nan_temporal_reduce_varlen: frames must be float32 [sum T, ...]")
+    _require(offsets.dim() == 1 and offsets.numel() >= 1, "nan_temporal_reduce_varlen: offsets must be [V+1]")
+    _require(avg_method in (0, 1), "nan_temporal_reduce_varlen: avg_method must be 0 (median) or 1 (mean)")
+    offs = offsets.detach().to("cpu", torch.int64).contiguous()
+    V = offs.numel() - 1
+    _require(int(offs[0]) >= 0 and int(offs[-1]) <= frames.shape[0], "nan_temporal_reduce_varlen: offsets out of range")
+    frames = frames.contiguous()
+    out = torch.empty((V,) + tuple(frames.shape[1:]), dtype=torch.uint8, device=frames.device)
+    optr = ctypes.cast(offs.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+    with torch.cuda.device(frames.device):
+        _cabi.check(_cabi.lib().bgd_nan_temporal_reduce_varlen_f32(
+            frames.data_ptr(), optr, V, math.prod(frames.shape[1:]), int(avg_method), int(bool(zero_is_missing)),
+            out.data_ptr(), None, _stream_ptr(frames.device)))
+    return out
+
+
+@nan_temporal_reduce_varlen.register_fake
+def _(frames, offsets, avg_method, zero_is_missing):
+    return frames.new_empty((offsets.shape[0] - 1,) + tuple(frames.shape[1:]), dtype=torch.uint8)
+
+
+@torch.library.custom_op("bgdebias::nan_temporal_reduce_f32", mutates_args=(), device_types="cuda")
+def nan_temporal_reduce_f32(frames: torch.Tensor, avg_method: int, zero_is_missing: bool) -> torch.Tensor:
+    """The float32 reduction before the uint8 cast (NaN where no frame is valid)."""
+    return _nan_reduce(frames, avg_method, zero_is_missing, True)
+
+
+@nan_temporal_reduce_f32.register_fake
+def _(frames, avg_method, zero_is_missing):
+    return frames.new_empty(frames.shape[1:])
+
+
+# --------------------------------------------------------------------------- #
 # BG-mix blend
 # --------------------------------------------------------------------------- #
 def _host3(t: torch.Tensor, name: str):

@@ -100,6 +100,25 @@ int bgd_temporal_median_u8_host(const uint8_t *const *h_frame_ptrs, int64_t T, i
 int bgd_temporal_median_varlen_u8_host(const uint8_t *h_frames, const int64_t *h_offsets,
                                        int64_t V, int64_t N, uint8_t *h_out, int device);
 
+/* ---- NaN-masked temporal median / mean (simulated-camera-motion extraction) ---------------
+ * Replaces   ave_frame = np.nanmedian(transform_frames, axis=0).astype(np.uint8)   (avg_method 0)
+ *            ave_frame = np.nanmean(transform_frames, axis=0).astype(np.uint8)     (avg_method 1)
+ *   cil_tools/extract_background.py:94-98 (sim_cam_motion_bg_extract, :78-99); with zero_is_missing != 0
+ *   also the `frame[frame == 0] = np.nan` of :91.
+ * d_frames [T][N] float32 (N = 100*100*3 after RandomResizedCrop(100)); NaN (and 0) = missing.
+ * Median of n valid values: f32((s[(n-1)/2] + s[n/2]) / 2); mean: float32 running sum in frame order,
+ * f32(f64(sum) / f64(n)); n == 0: NaN.  d_out_u8 [N] receives the uint8 cast (truncation, NaN -> 0; the
+ * value domain is 0 <= v < 256), d_out_f32 [N] the float result; either may be NULL. */
+int bgd_nan_temporal_reduce_f32(const float *d_frames, int64_t T, int64_t N, int avg_method,
+                                int zero_is_missing, uint8_t *d_out_u8, float *d_out_f32, void *stream);
+
+/* V frame folders in one launch: d_frames [sum T][N], video v = rows h_offsets[v] .. h_offsets[v+1]-1 (HOST
+ * array of V+1 row indices, V <= 65535), outputs [V][N].  What bg_extract_multiple
+ * (extract_background.py:102-109) does folder by folder with --method sim_cam. */
+int bgd_nan_temporal_reduce_varlen_f32(const float *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
+                                       int avg_method, int zero_is_missing, uint8_t *d_out_u8,
+                                       float *d_out_f32, void *stream);
+
 /* ---- BG-mix blend ------------------------------------------------------------------------
  * Replaces, for a whole batch in one launch,
  *   libs/loader/comix_loader.py:138-145   BackgroundMixDataset._mix_background

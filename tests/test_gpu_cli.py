@@ -83,5 +83,3 @@ def test_per_video_functions_keep_the_reference_signatures(tmp_path):
     assert (tmp_path / "f.jpg").exists()
     with pytest.raises(NotImplementedError):
         cl.bg_extraction_tmf(folder, tmp_path / "g.jpg", from_video=True)
-    with pytest.raises(NotImplementedError):
-        eb.sim_cam_motion_bg_extract(tmp_path / "v.avi", tmp_path / "s.jpg", True, 1, 10, 0)
