@@ -18,7 +18,10 @@ on its original device.  Works with ``num_workers=0`` or CUDA-capable workers.
 ``device_mix=True`` (the fast path): the pipeline stops before ``Normalize`` and yields uint8 frames
 ``[T,H,W,3]``; ``prepare_train_frames`` only draws the parameters (``bg_idx``, ``bg_top``,
 ``bg_left``, ``bg_apply``) and ``BackgroundMixDataset.gpu_collate`` / ``mix_batch_on_device`` turns a
-collated uint8 batch into the fp32 training tensor ``[B,T,3,H,W]`` with one kernel launch.
+collated uint8 batch into the fp32 training tensor ``[B,T,3,H,W]`` with one kernel launch.  With DataLoader
+worker processes use ``collate_fn=dataset.host_collate`` (host tensors only, safe after ``fork``) and call
+``dataset.device_finish(batch)`` in the training process: the batch crosses PCIe as uint8, a quarter of the
+reference's fp32 bytes.
 """
 from __future__ import annotations
 
@@ -340,21 +343,37 @@ class BackgroundMixDataset(_Base):
             self._resized_cache[key] = ops.make_fg_lut(mean, std, self.device)
         return self._resized_cache[key]
 
-    def gpu_collate(self, samples: List[dict]) -> dict:
-        """``collate_fn`` for ``device_mix=True``: stacks the uint8 clips, runs the fused blend once and
-        returns the dict the reference's default_collate would (``imgs`` fp32 [B,T,3,H,W], ``label``,
-        ``randAug``, ``bg_idx``)."""
-        fg = torch.stack([torch.as_tensor(s['imgs']) for s in samples])
+    @staticmethod
+    def host_collate(samples: List[dict]) -> dict:
+        """``collate_fn`` for ``device_mix=True`` that is safe in DataLoader worker processes (no CUDA): stacks
+        the uint8 clips ``[B,T,H,W,3]`` and the per-sample draws into host tensors.  Pair it with
+        :meth:`device_finish` in the training process; with ``pin_memory=True`` the batch travels as uint8,
+        a quarter of the bytes of the reference's fp32 batch (libs/cil/cil.py:203-210)."""
         out = {
-            'imgs': self.mix_batch_on_device(fg, [s['bg_idx'] for s in samples], [s['bg_top'] for s in samples],
-                                             [s['bg_left'] for s in samples], [s['bg_apply'] for s in samples]),
-            'bg_idx': torch.tensor([s['bg_idx'] for s in samples]),
+            'imgs': torch.stack([torch.as_tensor(s['imgs']) for s in samples]),
+            'bg_idx': torch.tensor([int(s['bg_idx']) for s in samples], dtype=torch.int64),
+            'bg_top': torch.tensor([int(s['bg_top']) for s in samples], dtype=torch.int32),
+            'bg_left': torch.tensor([int(s['bg_left']) for s in samples], dtype=torch.int32),
+            'bg_apply': torch.tensor([int(s['bg_apply']) for s in samples], dtype=torch.uint8),
         }
         if 'label' in samples[0]:
             out['label'] = torch.stack([torch.as_tensor(s['label']) for s in samples])
         if 'randAug' in samples[0]:
             out['randAug'] = torch.tensor([bool(s['randAug']) for s in samples])
         return out
+
+    def device_finish(self, batch: dict, layout: str = "NTCHW") -> dict:
+        """The GPU half of the ``device_mix=True`` path: turns a :meth:`host_collate` batch into the dict the
+        reference's default_collate would hand the model (``imgs`` fp32 ``[B,T,3,H,W]`` on the device, ``label``,
+        ``randAug``, ``bg_idx``) with one fused launch."""
+        out = {k: v for k, v in batch.items() if k not in ('imgs', 'bg_top', 'bg_left', 'bg_apply')}
+        out['imgs'] = self.mix_batch_on_device(batch['imgs'], batch['bg_idx'], batch['bg_top'], batch['bg_left'],
+                                               batch['bg_apply'], layout=layout)
+        return out
+
+    def gpu_collate(self, samples: List[dict]) -> dict:
+        """:meth:`host_collate` + :meth:`device_finish` in one call, for ``num_workers=0`` loaders."""
+        return self.device_finish(self.host_collate(samples))
 
 
 def bg_extraction_tmf(data_path, dest, from_video=False, device='cuda'):

@@ -332,3 +332,55 @@ def test_pool_lifecycle_across_tasks(env):
         run(list(set(task0) | set(merged)), 4)
         assert len(calls) == 9 + probes
         assert len(ds._store) == 9 and ds._store.decoded == 9
+
+
+class _U8Pipeline:
+    """Picklable stand-in for the mmaction pipeline up to (not including) Normalize: uint8 [T,H,W,3] clips."""
+    def __init__(self, fg, ra):
+        self.fg, self.ra = fg, ra
+
+    def __call__(self, info):
+        return dict(imgs=torch.from_numpy(self.fg[info["sample"]]), label=torch.tensor([info["label"]]),
+                    randAug=bool(self.ra[info["sample"]]))
+
+
+class _Reader:
+    def __init__(self, table):
+        self.table = table
+
+    def __call__(self, path):
+        return self.table[path]
+
+
+def test_dataloader_workers_then_device_finish(env, tmp_path):
+    """device_mix=True behind a real torch DataLoader with worker processes: workers draw and stack on the
+    host (no CUDA there), the training process blends once per batch.  Output = oracle blend of the draws."""
+    ops, cabi, cl, pool_mod = env
+    rng = np.random.default_rng(17)
+    T, H, W, n_bg, n = 2, 32, 32, 5, 12
+    fg = rng.integers(0, 256, (n, T, H, W, 3), dtype=np.uint8)
+    ra = rng.integers(0, 2, n).astype(bool)
+    names = [f"v{i:02d}" for i in range(n_bg)]
+    for nm in names:
+        (tmp_path / (nm + ".jpg")).write_bytes(b"stub")
+    table = {str((tmp_path / (nm + ".jpg")).resolve()): rng.integers(0, 256, (3, 36, 48), dtype=np.uint8) for nm in names}
+    infos = [dict(frame_dir=f"/x/{names[i % n_bg]}", total_frames=T, label=i, sample=i) for i in range(n)]
+    ds = cl.BackgroundMixDataset(infos, _U8Pipeline(fg, ra), bg_dir=str(tmp_path), bg_resize=40, bg_crop_size=(H, W),
+                                 with_randAug=True, device_mix=True, bg_reader=_Reader(table))
+    ds._pool_hw()                                             # size probe once, before the workers fork
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=2, collate_fn=ds.host_collate,
+                                         pin_memory=True)
+    seen = 0
+    for batch in loader:
+        assert batch["imgs"].dtype == torch.uint8 and not batch["imgs"].is_cuda
+        out = ds.device_finish(batch)
+        B = batch["imgs"].shape[0]
+        idx = batch["bg_idx"].tolist()
+        resized = np.stack([bo.bg_resize(table[p], 40).numpy() for p in ds.bg_files])
+        exp = bo.mix_batch(fg[seen:seen + B], resized, [max(i, 0) for i in idx], batch["bg_top"].tolist(),
+                           batch["bg_left"].tolist(), batch["bg_apply"].tolist(), crop=(H, W))
+        _assert_same(out["imgs"].cpu().numpy(), exp)
+        assert out["imgs"].is_cuda and [(i == -1) for i in idx] == list(ra[seen:seen + B])
+        assert set(out) == {"imgs", "bg_idx", "label", "randAug"}
+        seen += B
+    assert seen == n
