@@ -163,6 +163,20 @@ def mix_batch(fg_u8_bthwc: np.ndarray, pool_resized: np.ndarray, bg_idx: Sequenc
     return out
 
 
+def mix_clip_like_reference(imgs, bg_u8_chw, alpha: float = 0.5, bg_resize_size: int = 256, crop=(224, 224),
+                            mean: Sequence[float] = DEFAULT_MEAN, std: Sequence[float] = DEFAULT_STD):
+    """``_mix_background`` with the libraries the reference calls (comix_loader.py:72-75,139-142): torchvision
+    ``Compose([Resize, RandomCrop, Normalize])`` on the float background, then the torch blend.  ``imgs``: fp32
+    torch tensor ``[T,3,H,W]`` (already normalised); consumes the torch RNG for the crop.  Used as the CPU arm
+    of bench.py's BG-mix leg and to cross-check :func:`mix_clip`."""
+    import torch
+    from torchvision.transforms import Compose, Normalize, RandomCrop, Resize
+    pipe = Compose([Resize(bg_resize_size), RandomCrop(tuple(crop)), Normalize(mean=list(mean), std=list(std))])
+    bg = pipe(torch.as_tensor(bg_u8_chw).float())
+    bg = bg.view(1, 3, crop[0], crop[1])
+    return imgs * (1 - alpha) + bg * alpha
+
+
 def gate(with_randAug: bool, randAug_flag: bool, prob: float, rand_value: float) -> bool:
     """Whether a sample is mixed (comix_loader.py:111-116); ``rand_value`` = ``random.random()``
     (drawn only when ``with_randAug`` is False)."""

@@ -101,3 +101,24 @@ def test_layouts():
     b = bo.mix_batch(fg, pool, [1, 0], [2, 0], [1, 3], [1, 0], crop=(8, 8), layout="NCTHW")
     assert a.shape == (2, 3, 3, 8, 8) and b.shape == (2, 3, 3, 8, 8)
     np.testing.assert_array_equal(a.transpose(0, 2, 1, 3, 4), b)
+
+
+def test_restated_arithmetic_equals_the_library_calls_of_the_reference():
+    """mix_clip (the arithmetic the CUDA kernel implements, restated operation by operation) is bit-identical to
+    the reference's own expression evaluated with torchvision + torch (comix_loader.py:72-75,139-142)."""
+    import numpy as np
+    import torch
+    from oracle import bgmix_oracle as bo
+    rs = np.random.default_rng(3)
+    fg_u8 = rs.integers(0, 256, (4, 224, 224, 3), dtype=np.uint8)
+    bg = rs.integers(0, 256, (3, 240, 320), dtype=np.uint8)
+    fgn = torch.from_numpy(bo.fg_normalize(fg_u8, bo.fg_lut()))
+    for alpha in (0.5, 0.3):
+        torch.manual_seed(7)
+        a = bo.mix_clip_like_reference(fgn, torch.from_numpy(bg), alpha).numpy()
+        torch.manual_seed(7)
+        r = bo.bg_resize(bg, 256).numpy()
+        top = int(torch.randint(0, r.shape[1] - 224 + 1, (1,)))
+        left = int(torch.randint(0, r.shape[2] - 224 + 1, (1,)))
+        b = bo.mix_clip(fg_u8, r, top, left, alpha=alpha)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
