@@ -372,10 +372,15 @@ def run_ours(args):
             except Exception as e:
                 mix_cpu = {"value": None, "unit": "clips/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(e)}
         peak, _ = measured_peak_gbs()
+        mix_traffic = None
+        try:
+            mix_traffic = json.loads((ROOT / "profiles" / "r1_traffic_bgmix.json").read_text())["dram_bytes_per_algorithmic_byte"] * mix_bytes
+        except Exception:
+            pass
         bgmix = {"metric": "bgmix_clips_per_sec", "value": world * B / (mix_ms * 1e-3), "unit": "clips/s",
                  "ms_per_step": mix_ms, "config": {"workload": "configs[4]: fg u8 [64,8,224,224,3], fp32 pool 1024x3x256x341, alpha 0.5, all samples mixed, out fp32 [64,8,3,224,224]", "l2": "256 MB flush write between iterations"},
                  "roofline": {"bound": "hbm", "achieved": mix_bytes / (mix_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": mix_bytes / (mix_ms * 1e-3) / 1e9 / peak, "traffic": None},
+                              "frac": mix_bytes / (mix_ms * 1e-3) / 1e9 / peak, "traffic": mix_traffic},
                  "e2e": {"value": world * mix_e2e, "unit": "clips/s", "h2d_bytes_per_step": int(h_fg.numel() + B * 13),
                          "d2h_bytes_per_step": 8},
                  "cpu_baseline": mix_cpu,
