@@ -130,7 +130,7 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
 
     const int variant = g_variant.load();
     const bool aligned = reinterpret_cast<uintptr_t>(d_frames) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
-    const bool can_col = aligned && median_colplane_supports(T_max, N);
+    const bool can_col = aligned && median_tma_supports(T_max, N);
     const bool can_bit = aligned && median_bitsliced_supports(T_max, N);
     if (((variant == BGD_MEDIAN_COLPLANE || variant == BGD_MEDIAN_LDSM) && !can_col) || (variant == BGD_MEDIAN_BITSLICED && !can_bit))
         return fail(BGD_ERR_UNSUPPORTED,
@@ -138,7 +138,7 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
                     (long long)T_max, (long long)N);
     // AUTO / LDSM: videos of up to 512 frames take the transposing-load kernel, longer ones the column-plane kernel
     if (variant == BGD_MEDIAN_COLPLANE || variant == BGD_MEDIAN_LDSM || (variant == BGD_MEDIAN_AUTO && can_col))
-        return median_colplane_varlen(d_frames, h_offsets, V, N, d_out, variant != BGD_MEDIAN_COLPLANE, stream);
+        return median_tma_varlen(d_frames, h_offsets, V, N, d_out, variant != BGD_MEDIAN_COLPLANE, stream);
     if (variant == BGD_MEDIAN_BITSLICED || (variant == BGD_MEDIAN_AUTO && can_bit))
         return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
 

@@ -49,9 +49,9 @@ struct MedianWork;  // planner output, see median_bitsliced.cu
 int median_bitsliced_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
                             uint8_t *d_out, cudaStream_t stream);
 bool median_bitsliced_supports(int64_t T_max, int64_t N);
-int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
+int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N,
                            uint8_t *d_out, bool use_ldsm, cudaStream_t stream);
-bool median_colplane_supports(int64_t T_max, int64_t N);
+bool median_tma_supports(int64_t T_max, int64_t N);
 
 int launch_bgmix(const uint8_t *d_fg, const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W, const void *d_pool,
                  bool pool_is_u8, int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx,

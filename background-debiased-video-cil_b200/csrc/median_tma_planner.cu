@@ -1,5 +1,6 @@
-// Host side of the column-plane median (see median_colplane.cuh): bucket the videos of a call by
-// kernel configuration (C, NW, parity), build the TMA tensor maps, launch one kernel per bucket.
+// Host side of the two TMA-staged medians (median_ldsm.cuh for T <= 512, median_colplane.cuh above): bucket
+// the videos of a call by kernel configuration (kernel family, plane groups, parity), build the TMA tensor
+// maps, upload one table of (first row, frame count, output slot) per video and launch one kernel per bucket.
 #include <algorithm>
 #include <map>
 #include <tuple>
@@ -86,7 +87,7 @@ int get_encode_fn(EncodeTiledFn *out)
 
 }  // namespace
 
-bool median_colplane_supports(int64_t T_max, int64_t N)
+bool median_tma_supports(int64_t T_max, int64_t N)
 {
     if (N <= 0 || N % 16 != 0 || N >= ((int64_t)1 << 31)) return false;
     if (T_max < 1 || T_max > 544) return false;
@@ -94,7 +95,7 @@ bool median_colplane_supports(int64_t T_max, int64_t N)
     return classify((int)T_max, read_tuning(), false, &k);
 }
 
-int median_colplane_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, uint8_t *d_out,
+int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, uint8_t *d_out,
                            bool use_ldsm, cudaStream_t stream)
 {
     if (V == 0 || N == 0) return BGD_OK;
