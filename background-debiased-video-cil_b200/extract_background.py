@@ -21,8 +21,10 @@ readable image (``if img:`` on an ndarray, :67-68); here it reads the images as 
 from __future__ import annotations
 
 import argparse
+import json
 import pathlib
 import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import List
 
@@ -227,8 +229,50 @@ def main(argv=None):
         raise ValueError
 
     splits = _shard.contiguous_splits(video_paths, args.num_workers)
+    t0 = time.perf_counter()
     _shard.run_shards(_shard_entry, splits, str(output_dir), args.from_video, args.interval, args.max_frames,
                       args.method, avg_method, args.decode_threads, args.slab_mb)
+    seconds = time.perf_counter() - t0
+    index = write_background_index(output_dir, args.image_suffix)
+    # one line of run metrics (the reference reports nothing for this path)
+    print(json.dumps({"extracted": len(video_paths), "skipped_existing": len(extracted), "backgrounds_indexed": len(index),
+                      "seconds": round(seconds, 3), "videos_per_s": round(len(video_paths) / seconds, 2) if seconds > 0 else None,
+                      "shards": sum(1 for s_ in splits if len(s_)), "method": args.method}))
+
+
+INDEX_SUFFIX = ".bg_index.json"
+
+
+def index_path(output_dir: pathlib.Path) -> pathlib.Path:
+    """``<output_dir>.bg_index.json`` BESIDE the directory, not in it: the reference's Places365-style pools take
+    every file of ``bg_dir`` as a background (``glob('*')``, comix_loader.py:100-101), so nothing else may live there."""
+    output_dir = pathlib.Path(output_dir)
+    return output_dir.parent / (output_dir.name + INDEX_SUFFIX)
+
+
+def write_background_index(output_dir: pathlib.Path, image_suffix: str = '.jpg') -> list:
+    """Persist the background index beside the JPEG folder: ``[{"name", "file", "height", "width"}, ...]`` sorted by
+    name -- the pool order ``BackgroundMixDataset(map_bg_to_video=False)`` and ``BackgroundPool.from_index`` use, so
+    a mix pool can be rebuilt (and all-gathered by name) without touching the videos again.  Rewritten from the
+    directory listing on every run, so it also covers backgrounds kept by the skip-if-exists resume."""
+    output_dir = pathlib.Path(output_dir)
+    entries = []
+    for f in sorted(output_dir.glob('*' + image_suffix)):
+        ok, w, h = _image_size(f)
+        if ok:
+            entries.append({"name": f.stem, "file": f.name, "height": h, "width": w})
+    dest = index_path(output_dir)
+    tmp = dest.with_name(dest.name + ".tmp")
+    tmp.write_text(json.dumps(entries))
+    tmp.replace(dest)                               # atomic: a crashed run never leaves half an index
+    return entries
+
+
+def _image_size(path: pathlib.Path):
+    img = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+    if img is None:
+        return False, 0, 0
+    return True, int(img.shape[1]), int(img.shape[0])
 
 
 if __name__ == '__main__':

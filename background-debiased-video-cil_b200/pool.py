@@ -91,6 +91,20 @@ class BackgroundPool:
         imgs = [read_image(str(f), mode=ImageReadMode.RGB) for f in bg_files]
         return cls.from_images(imgs, [str(f) for f in bg_files], bg_resize, device)
 
+    @classmethod
+    def from_index(cls, bg_dir, bg_resize: Optional[int] = 256, device="cuda") -> "BackgroundPool":
+        """Rebuild the pool from the index the extraction CLI writes beside its JPEG folder
+        (``extract_background.write_background_index``, ``<bg_dir>.bg_index.json``): same order on every rank,
+        no video is read."""
+        import json
+        import pathlib
+        bg_dir = pathlib.Path(bg_dir)
+        index = bg_dir.parent / (bg_dir.name + ".bg_index.json")
+        entries = json.loads(index.read_text())
+        if not entries:
+            raise ValueError(f"{index} lists no backgrounds")
+        return cls.from_files([str(bg_dir / e["file"]) for e in entries], bg_resize, device)
+
     # ---- one collective: assemble the pool from per-rank shards (SURVEY.md section 8e) ----------
     @staticmethod
     def all_gather(local_names: Sequence[str], local_bgs: torch.Tensor, group=None):

@@ -51,6 +51,15 @@ def test_cli_folder_of_videos(tmp_path, workers):
     for name, fr in videos.items():
         got = (odir / f"{name}.jpg").read_bytes()
         assert got == _expected_jpeg(list(fr), 2, 10, tmp_path), name
+    # the index persisted next to the JPEGs: sorted names + sizes; the pool can be rebuilt from it alone
+    import json
+    assert sorted(p.name for p in odir.iterdir()) == sorted(f"{n}.jpg" for n in videos)      # nothing but backgrounds in bg_dir
+    index = json.loads(eb.index_path(odir).read_text())
+    assert [e["name"] for e in index] == sorted(videos) and all((e["height"], e["width"]) == (H, W) for e in index)
+    from bgdebias_b200.pool import BackgroundPool
+    pool = BackgroundPool.from_index(odir, bg_resize=None)
+    assert len(pool) == len(videos) and pool.hw == (H, W)
+    assert [pathlib.Path(n).stem for n in pool.names] == sorted(videos)
     # resume: existing outputs are skipped, not rewritten
     marker = odir / "a.jpg"
     marker.write_bytes(b"kept")
