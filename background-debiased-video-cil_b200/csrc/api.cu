@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "bgd_common.cuh"
@@ -253,6 +254,16 @@ static bool is_pinned_host(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
+static int pack_threads()
+{
+    static const int n = [] {
+        if (const char *s = getenv("BGD_PACK_THREADS")) return std::max(1, std::min(32, atoi(s)));
+        const unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(8u, hc / 2));
+    }();
+    return n;
+}
+
 static size_t staging_slab_bytes()
 {
     size_t mb = 256;
@@ -316,20 +327,35 @@ static int median_host_pipeline(const uint8_t *const *frame_ptrs, const uint8_t 
         if (int rc = drain(slot)) return rc;
         const int64_t v0 = chunks[ci].first, v1 = chunks[ci].second;
         const int64_t r0 = h_offsets[v0], r1 = h_offsets[v1];
-        const uint8_t *src = nullptr;
-        if (in_pinned) {
-            src = frames + (size_t)r0 * N;
-        } else {
-            // pack the chunk into the pinned slab (gathers separately allocated frames)
-            if (frame_ptrs) {
-                for (int64_t r = r0; r < r1; ++r) std::memcpy(st.h_in[slot] + (size_t)(r - r0) * N, frame_ptrs[r], (size_t)N);
-            } else {
-                std::memcpy(st.h_in[slot], frames + (size_t)r0 * N, (size_t)(r1 - r0) * N);
-            }
-            src = st.h_in[slot];
-        }
         cudaStream_t s = st.stream[slot];
-        BGD_CUDA_TRY(cudaMemcpyAsync(st.d_in[slot], src, (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, s));
+        if (in_pinned) {
+            BGD_CUDA_TRY(cudaMemcpyAsync(st.d_in[slot], frames + (size_t)r0 * N, (size_t)(r1 - r0) * N, cudaMemcpyHostToDevice, s));
+        } else {
+            // pack the chunk into the pinned slab (gathers separately allocated frames) with a few threads, and
+            // send each part as soon as it is packed: the DMA of part i overlaps the packing of part i + 1
+            const int64_t rows = r1 - r0;
+            const size_t bytes = (size_t)rows * N;
+            int parts = bytes >= ((size_t)8 << 20) ? (int)std::min<int64_t>(pack_threads(), rows) : 1;
+            std::vector<std::thread> workers;
+            auto pack = [&](int64_t a, int64_t b) {
+                if (frame_ptrs) {
+                    for (int64_t r = a; r < b; ++r) std::memcpy(st.h_in[slot] + (size_t)(r - r0) * N, frame_ptrs[r], (size_t)N);
+                } else {
+                    std::memcpy(st.h_in[slot] + (size_t)(a - r0) * N, frames + (size_t)a * N, (size_t)(b - a) * N);
+                }
+            };
+            std::vector<int64_t> cut((size_t)parts + 1);
+            for (int p = 0; p <= parts; ++p) cut[(size_t)p] = r0 + rows * p / parts;
+            for (int p = 1; p < parts; ++p) workers.emplace_back(pack, cut[(size_t)p], cut[(size_t)p + 1]);
+            pack(cut[0], cut[1]);
+            cudaError_t err = cudaSuccess;
+            for (int p = 0; p < parts; ++p) {
+                if (p > 0) workers[(size_t)p - 1].join();
+                const size_t off = (size_t)(cut[(size_t)p] - r0) * N, len = (size_t)(cut[(size_t)p + 1] - cut[(size_t)p]) * N;
+                if (err == cudaSuccess && len) err = cudaMemcpyAsync(st.d_in[slot] + off, st.h_in[slot] + off, len, cudaMemcpyHostToDevice, s);
+            }
+            if (err != cudaSuccess) return fail(BGD_ERR_CUDA, "cudaMemcpyAsync (frames to device) failed: %s", cudaGetErrorString(err));
+        }
         local.resize((size_t)(v1 - v0 + 1));
         for (int64_t v = v0; v <= v1; ++v) local[(size_t)(v - v0)] = h_offsets[v] - r0;
         if (int rc = median_varlen_dispatch(st.d_in[slot], local.data(), v1 - v0, N, st.d_out[slot], s)) return rc;
