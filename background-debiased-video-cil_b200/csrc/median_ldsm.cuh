@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
             const int col = ct * kTileW + s * kStripW;
             uint8_t *dst = buf_s + (size_t)s * strip_bytes;
             int r = 0;
-            if (T >= 256) {
-                tma_load_2d(dst, &prm.maps[8], col, (int)row0, bar_s, policy);
-                r = 256;
+            while (T - r >= 256) {                       // T = 512 needs two of them
+                tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[8], col, (int)(row0 + r), bar_s, policy);
+                r += 256;
             }
 #pragma unroll
             for (int k = 7; k >= 0; --k)

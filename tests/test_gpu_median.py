@@ -56,7 +56,7 @@ def test_golden_reference_outputs(bgd, name, variant):
 
 
 T_VALUES = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 96, 100, 127, 128, 129,
-            179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 527, 528, 543, 544, 576]
+            179, 180, 181, 239, 240, 255, 256, 257, 300, 383, 384, 385, 500, 501, 511, 512, 513, 527, 528, 543, 544, 576]
 
 
 @pytest.mark.parametrize("variant", ["swar", "bitsliced", "colplane", "ldsm"])
