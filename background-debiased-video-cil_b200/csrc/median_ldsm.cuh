@@ -92,6 +92,13 @@ __device__ __forceinline__ int popc_acc(uint32_t x, int acc, uint32_t one)
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(__popc(x)), "r"(one), "r"(acc));
     return r;
 }
+// a * b + c issued as IMAD (FMA pipe); the callers pass run-time operands the compiler cannot fold
+__device__ __forceinline__ int imad(int a, int b, int c)
+{
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 // (a & mask) | (b & ~mask)
 __device__ __forceinline__ int isel(int a, int b, int mask)
 {
@@ -281,7 +288,11 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
             }
             int rank = (T - 1) >> 1;                     // 0-based rank of the lower middle among the alive rows
             int rc = rank - T;                           // rank - (number of alive rows), always negative
-            int lo = 0, hi = 0;
+            // The rank bookkeeping runs on the FMA pipe (IMAD with run-time 1 / -1 / 2 the compiler cannot fold):
+            // the LOP3 pipe is the one this kernel fills.  lo_acc / hi_acc collect  sum_b m_b 2^b  with m_b = -1
+            // where the bit is 0, so the value is 255 + acc.
+            const int ONE = (int)one, NEG1 = -(int)one, TWO = (int)one << 1;
+            int lo_acc = 0, hi_acc = 0;
             int diverged = 0;                            // all-ones once the two middles sit in different sets
 #pragma unroll
             for (int b = 7; b >= 0; --b) {
@@ -294,22 +305,24 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
                     for (int k = 0; k < NWC; ++k) any0 |= alive2[k] & ~plane(k, b);
                 }
                 const int m0 = d >> 31;                  // all-ones: rank < zeros, the bit is 0
-                rank = isel(rank, d, m0);
-                rc = isel(d, rc, m0);
-                lo |= ~m0 & (1 << b);
+                const int t1 = imad(m0, ONE, ONE);       // 1 where the bit is 1
+                rank = imad(imad(rank, NEG1, d), t1, rank);      // bit 1: rank - zeros (= d);  bit 0: unchanged
+                rc = imad(imad(d, NEG1, rc), t1, d);             // bit 1: unchanged;           bit 0: d
+                lo_acc = imad(lo_acc, TWO, m0);
 #pragma unroll
                 for (int k = 0; k < NWC; ++k) alive[k] &= plane(k, b) ^ (uint32_t)m0;
                 if (EVEN) {
                     // shared state: the upper middle has rank + 1, its bit is 0 iff d + 1 < 0; own state: iff any0
-                    const int m0_shared = (d + 1) >> 31;
-                    const int m0_own = any0 != 0u ? -1 : 0;
+                    const int m0_shared = imad(ONE, ONE, d) >> 31;
+                    const int m0_own = imad(__popc(any0), NEG1, 0) >> 31;
                     const int m2 = isel(m0_own, m0_shared, diverged);
                     diverged |= m2 ^ m0;
-                    hi |= ~m2 & (1 << b);
+                    hi_acc = imad(hi_acc, TWO, m2);
 #pragma unroll
                     for (int k = 0; k < NWC; ++k) alive2[k] &= plane(k, b) ^ (uint32_t)m2;
                 }
             }
+            const int lo = 255 + lo_acc, hi = 255 + hi_acc;
             med[c] = EVEN ? ((lo + hi) >> 1) : lo;
         }
 
