@@ -194,8 +194,10 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
             // buffers + mbarriers + slack to align the buffers to the 1024-byte swizzle atom; as many stages as
             // fit beside the CTA count the registers allow (1 KB per CTA is reserved by the driver)
             const size_t tile_bytes = (size_t)lprm.rows_cap * tile_w;
+            // CTAs per SM: what the registers allow (8 x 64 threads up to 192 frames, then 6, 3, 2); short videos
+            // need few registers and little shared memory and gain 3-5 % from up to 16 (profiles/r1_sweep_ldsm_blocks.txt)
             const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks
-                               : (key.NW <= 12 ? 8 : (key.NW <= ldsm::kMaxNH ? 6 : (key.NW <= 24 ? 3 : 2))) / lprm.strips;
+                               : (key.NW <= 6 ? 16 : (key.NW <= 12 ? 8 : (key.NW <= ldsm::kMaxNH ? 6 : (key.NW <= 24 ? 3 : 2)))) / lprm.strips;
             const size_t per_block = (size_t)dp.smem_per_sm / blocks - 1024;
             int stages = tn.ldsm_stages > 0 ? tn.ldsm_stages : (int)((per_block - 1024 - 64) / tile_bytes);
             stages = std::max(1, std::min(stages, tn.ldsm_stages > 0 ? 8 : 4));
