@@ -286,17 +286,19 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
                 alive[k] = k == NWC - 1 ? (HALF ? last_mask << (4 * c) : last_mask) : 0xFFFFFFFFu;
                 if (EVEN) alive2[k] = alive[k];
             }
-            int rank = (T - 1) >> 1;                     // 0-based rank of the lower middle among the alive rows
-            int rc = rank - T;                           // rank - (number of alive rows), always negative
-            // The rank bookkeeping runs on the FMA pipe (IMAD with run-time 1 / -1 / 2 the compiler cannot fold):
-            // the LOP3 pipe is the one this kernel fills.  lo_acc / hi_acc collect  sum_b m_b 2^b  with m_b = -1
-            // where the bit is 0, so the value is 255 + acc.
+            // State of the select: rc = rank - (number of alive rows), always negative, where rank is the 0-based
+            // rank of the lower middle among the alive rows.  With `ones` alive rows having the bit set,
+            // d = rc + ones = rank - zeros decides the bit (0 iff d < 0), and the new rc is d for bit 0 (the zeros
+            // stay alive) and unchanged for bit 1 (rank and the alive count both drop by zeros): rank itself
+            // never has to be kept.  lo_acc / hi_acc collect  sum_b m_b 2^b  with m_b = -1 where the bit is 0 (IMAD,
+            // FMA pipe: the LOP3 pipe is the one this kernel fills), so the value is 255 + acc.
+            int rc = ((T - 1) >> 1) - T;
             const int ONE = (int)one, NEG1 = -(int)one, TWO = (int)one << 1;
             int lo_acc = 0, hi_acc = 0;
             int diverged = 0;                            // all-ones once the two middles sit in different sets
 #pragma unroll
             for (int b = 7; b >= 0; --b) {
-                int d = rc;                              // becomes rank - zeros
+                int d = rc;
 #pragma unroll
                 for (int k = 0; k < NWC; ++k) d = popc_acc(alive[k] & plane(k, b), d, one);
                 uint32_t any0 = 0u;                      // rows of the upper middle's set whose bit is 0
@@ -304,10 +306,8 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
 #pragma unroll
                     for (int k = 0; k < NWC; ++k) any0 |= alive2[k] & ~plane(k, b);
                 }
-                const int m0 = d >> 31;                  // all-ones: rank < zeros, the bit is 0
-                const int t1 = imad(m0, ONE, ONE);       // 1 where the bit is 1
-                rank = imad(imad(rank, NEG1, d), t1, rank);      // bit 1: rank - zeros (= d);  bit 0: unchanged
-                rc = imad(imad(d, NEG1, rc), t1, d);             // bit 1: unchanged;           bit 0: d
+                const int m0 = d >> 31;                  // all-ones: the bit is 0
+                rc = isel(d, rc, m0);
                 lo_acc = imad(lo_acc, TWO, m0);
 #pragma unroll
                 for (int k = 0; k < NWC; ++k) alive[k] &= plane(k, b) ^ (uint32_t)m0;
