@@ -227,15 +227,16 @@ __global__ void __launch_bounds__(kNanThreads) nan_median_planes_kernel(const fl
     if (nvalid == 0) {
         res = __uint_as_float(0x7FC00000u);
     } else {
-        int rank = (nvalid - 1) >> 1;                    // 0-based rank of the lower middle among the alive rows
-        int rc = rank - nvalid;                          // rank - (number of alive rows), always negative
+        // rc = rank - (number of alive rows), always negative; rank = 0-based rank of the lower middle among the
+        // alive rows.  d = rc + ones = rank - zeros decides the bit; rc becomes d for bit 0, stays for bit 1.
+        int rc = ((nvalid - 1) >> 1) - nvalid;
         uint32_t lo = 0u, hi = 0u;
         int diverged = 0;                                // all-ones once the two middles sit in different sets
         const uint32_t *pl = planes + 31 * kNanThreads;   // plane b of group 0; group k is k * 32 planes further
 #pragma unroll 4
         for (int b = 31; b >= 0; --b, pl -= kNanThreads) {
             uint32_t P[NW];
-            int d = rc;                                  // becomes rank - zeros
+            int d = rc;
             uint32_t any0 = 0u;                          // rows of the upper middle's set whose bit is 0
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
@@ -244,7 +245,6 @@ __global__ void __launch_bounds__(kNanThreads) nan_median_planes_kernel(const fl
                 any0 |= alive2[k] & ~P[k];
             }
             const int m0 = d >> 31;                      // all-ones: rank < zeros, the bit is 0
-            rank = isel32(rank, d, m0);
             rc = isel32(d, rc, m0);
             lo |= ~(uint32_t)m0 & (1u << b);
             const int m0_shared = (d + 1) >> 31;         // shared state: the upper middle has rank + 1
