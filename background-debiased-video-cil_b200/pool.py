@@ -117,6 +117,17 @@ class BackgroundPool:
             raise ValueError(f"{index} lists no backgrounds")
         return cls.from_files([str(bg_dir / e["file"]) for e in entries], bg_resize, device)
 
+    @staticmethod
+    def all_gather_index(local_names: Sequence[str], group=None) -> list:
+        """Index-only form of :meth:`all_gather` for pools too large to replicate (Sth-Sth-v2: ~68 GB of uint8
+        backgrounds): every rank learns ``[(name, owner_rank, slot_on_owner), ...]`` in rank order -- the global
+        pool index -- while the pixels stay sharded where they were extracted."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        names_per_rank: List[Optional[list]] = [None] * world
+        dist.all_gather_object(names_per_rank, list(local_names), group=group)
+        return [(n, r, i) for r, per in enumerate(names_per_rank) for i, n in enumerate(per)]
+
     # ---- one collective: assemble the pool from per-rank shards (SURVEY.md section 8e) ----------
     @staticmethod
     def all_gather(local_names: Sequence[str], local_bgs: torch.Tensor, group=None):

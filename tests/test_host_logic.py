@@ -124,6 +124,8 @@ def _gather_worker(rank, world, port, q):
     names = [f"r{rank}_v{i}" for i in range(n)]
     bgs = torch.full((n, 4, 5, 3), rank + 1, dtype=torch.uint8) + torch.arange(n, dtype=torch.uint8).view(n, 1, 1, 1)
     all_names, all_bgs = BackgroundPool.all_gather(names, bgs)
+    index = BackgroundPool.all_gather_index(names)
+    assert [n for n, _, _ in index] == all_names and [(r, i) for _, r, i in index] == [(0, 0), (0, 1), (0, 2), (1, 0)]
     q.put((rank, all_names, all_bgs.numpy()))
     dist.destroy_process_group()
 
