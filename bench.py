@@ -29,11 +29,31 @@ import time
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-H, W = 240, 320
-N_BYTES = H * W * 3
-VIDEOS_TOTAL, SHARDS = 13320, 8
-VIDEOS_PER_GPU = VIDEOS_TOTAL // SHARDS            # 1665
-T_LO, T_HI = 120, 241
+# The bench line is configs[1] (ucf101).  The other extraction configs of BASELINE.json are parity-test cases; they
+# can be timed through the same code with --workload (the JSON line then names that workload).
+WORKLOADS = {
+    "ucf101": dict(H=240, W=320, t_lo=120, t_hi=241, t_mul=1, videos=13320 // 8, t_text="U[120,240]",
+                   label="configs[1]: UCF101-shaped set, one 1/8 shard per GPU"),
+    "hmdb51": dict(H=240, W=320, t_lo=30, t_hi=81, t_mul=2, videos=846, t_text="2*U[30,80] (even)",
+                   label="configs[2]: HMDB51-shaped set (even T), one 1/8 shard per GPU"),
+    "sthv2": dict(H=240, W=427, t_lo=24, t_hi=73, t_mul=1, videos=4096, t_text="U[24,72]",
+                  label="configs[3]: Sth-Sth-v2-shaped clips, a resident 4,096-clip chunk of the 27,606-clip 1/8 shard"),
+}
+
+
+def _select_workload(name: str) -> None:
+    global WL, WL_NAME, H, W, N_BYTES
+    WL_NAME, WL = name, WORKLOADS[name]
+    H, W = WL["H"], WL["W"]
+    N_BYTES = H * W * 3
+    os.environ["BGD_BENCH_WORKLOAD"] = name          # spawned CPU-arm workers re-import this module
+
+
+def draw_T(rng, n=None):
+    return WL["t_mul"] * rng.integers(WL["t_lo"], WL["t_hi"], n)
+
+
+_select_workload(os.environ.get("BGD_BENCH_WORKLOAD", "ucf101"))
 
 
 def log(*a):
@@ -74,7 +94,7 @@ def _cpu_worker(args):
     rng = np.random.default_rng(seed)
     vids = []
     for _ in range(n_videos):
-        T = int(rng.integers(T_LO, T_HI))
+        T = int(draw_T(rng))
         vids.append([rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(T)])   # the `frames` list
     t0 = time.perf_counter()
     for frames in vids:
@@ -166,12 +186,12 @@ def run_reference(args):
         t_all += t
         f_all += frames
     value = f_all / t_all
-    sample = f"{procs} videos per step (one per process), T~U[120,240], 240x320x3, np.median only (no decode)"
+    sample = f"{procs} videos per step (one per process), T~{WL['t_text']}, {H}x{W}x3, np.median only (no decode)"
     emit({
         "impl": "reference", "metric": "bg_extraction_frames_per_sec", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "UCF101-shaped shard of configs[1] (T~U[120,240], 240x320x3 uint8); bounded sample per step",
+        "config": {"workload": WL["label"] + f" (T~{WL['t_text']}, {H}x{W}x3 uint8); bounded sample per step",
                    "videos_per_step": procs},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,9 +219,9 @@ def run_ours(args):
     _cabi.lib()
 
     # ---- the rank's shard, resident in HBM --------------------------------------------------
-    V = int(os.environ.get("BGD_BENCH_VIDEOS", VIDEOS_PER_GPU))
+    V = int(os.environ.get("BGD_BENCH_VIDEOS", WL["videos"]))
     rng = np.random.default_rng(1 + rank)
-    Ts = rng.integers(T_LO, T_HI, V)
+    Ts = draw_T(rng, V)
     free, _total = torch.cuda.mem_get_info(dev)
     while int(Ts.sum()) * N_BYTES + (4 << 30) > free and V > 16:          # another tenant on the GPU: shrink, say so
         V //= 2
@@ -415,9 +435,9 @@ def run_ours(args):
             "metric": "bg_extraction_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: UCF101-shaped set, one 1/8 shard per GPU", "videos_per_gpu": V,
-                       "frames_per_gpu": rows, "frame_shape": [H, W, 3], "T": "U[120,240]", "resident_gb": rows * N_BYTES / 1e9,
-                       "l2": "inputs (>60 GB per GPU) exceed L2; no flush needed", "kernel": "median_ldsm for T<=256, median_colplane above (AUTO)",
+            "config": {"workload": WL["label"], "videos_per_gpu": V,
+                       "frames_per_gpu": rows, "frame_shape": [H, W, 3], "T": WL["t_text"], "resident_gb": rows * N_BYTES / 1e9,
+                       "l2": "resident inputs (tens of GB per GPU) exceed L2; no flush needed", "kernel": "median_ldsm for T<=512, median_colplane above (AUTO)",
                        "parallelism": f"shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": rows_e * N_BYTES,
                     "d2h_bytes_per_step": Ve * N_BYTES, "videos_per_step": Ve, "parity": e2e_ok},
@@ -442,7 +462,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WL_NAME, choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    _select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:
