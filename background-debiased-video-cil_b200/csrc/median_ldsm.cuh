@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         }
     };
 
-    const bool producer = warp == 0 && elect_one();      // one lane of warp 0 issues the TMA copies
-    uint64_t policy = 0;
-    if (producer) policy = policy_evict_first();
+    // The warps of the CTA take turns at requesting tiles (one elected lane issues the TMA copies), so the
+    // ~150 instructions of a request are spread evenly instead of making warp 0 the one the others wait for.
+    constexpr int kWarps = threads_of<NH, STRIPS>() / 32;
+    const bool elected = elect_one();
+    const uint64_t policy = policy_evict_first();
     // Called by all lanes of warp 0 (the table reads are broadcast with SHFL so that ptxas sees warp-uniform
     // TMA operands and moves them to uniform registers without a per-value loop); the producer lane issues.
     auto issue_tile = [&](int vid, int ct, int slot) {
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         uint8_t *buf_s = buf + (size_t)slot * stage_bytes;
         const int T = __shfl_sync(0xFFFFFFFFu, prm.vid_T[vid], 0);
         const int row0 = __shfl_sync(0xFFFFFFFFu, (int)prm.vid_row0[vid], 0);
-        if (!producer) return;
+        if (!elected) return;
         mbar_arrive_expect_tx(bar_s, (uint32_t)T * (uint32_t)kTileW);
 #pragma unroll
         for (int s = 0; s < kTileW / kStripW; ++s) {
@@ -208,11 +210,12 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     int tile = blockIdx.x, vid = tile / tpv, ct = tile - vid * tpv;
     int ptile = tile, pvid = vid, pct = ct;              // the producer's cursor: `stages` tiles ahead
     for (int s = 0; s < stages; ++s) {
-        if (warp == 0 && ptile < num_tiles) issue_tile(pvid, pct, s);
+        if (warp == (s & (kWarps - 1)) && ptile < num_tiles) issue_tile(pvid, pct, s);
         advance(ptile, pvid, pct);
     }
 
     int slot = 0;
+    int turn = stages;                                   // whose turn it is to request a tile (continues the prologue's rotation)
     uint32_t phases = 0;                                 // bit s: parity to wait for on bar[s]
     for (; tile < num_tiles; advance(tile, vid, ct)) {
         const int T = prm.vid_T[vid];
@@ -248,11 +251,12 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         }
         __syncthreads();                                 // every lane has its columns: buffer is free
         {
-            if (warp == 0 && ptile < num_tiles) {
-                if (producer) fence_proxy_async();
+            if (warp == (turn & (kWarps - 1)) && ptile < num_tiles) {
+                if (elected) fence_proxy_async();
                 issue_tile(pvid, pct, slot);
             }
             advance(ptile, pvid, pct);
+            ++turn;
             slot = slot + 1 == stages ? 0 : slot + 1;
         }
 #pragma unroll
