@@ -229,3 +229,42 @@ def test_one_call_mixes_every_kernel_family(bgd):
     out = torch.ops.bgdebias.temporal_median_varlen(torch.from_numpy(fr).cuda(), torch.from_numpy(offs)).cpu().numpy()
     for v, T in enumerate(Ts):
         np.testing.assert_array_equal(out[v], c_oracle.temporal_median(fr[offs[v]:offs[v + 1]]), err_msg=f"T={T}")
+
+
+def test_concurrent_host_threads_and_streams(bgd):
+    """Four host threads, each on its own CUDA stream, call the op concurrently (ctypes releases the GIL during
+    the C-ABI call): per-thread workspaces and stream-ordered launches must not interfere."""
+    import threading
+    ops, cabi = bgd
+    cabi.set_median_variant(0)
+    rng = np.random.default_rng(31)
+    N = 4096 + 16
+    jobs = []
+    for i in range(4):
+        Ts = rng.integers(1, 300, 6)
+        offs = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+        fr = rng.integers(0, 256, (int(offs[-1]), N), dtype=np.uint8)
+        jobs.append((torch.from_numpy(fr).cuda(), torch.from_numpy(offs), fr, offs))
+    torch.cuda.synchronize()
+    results, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                outs = [torch.ops.bgdebias.temporal_median_varlen(jobs[i][0], jobs[i][1]) for _ in range(8)]
+            s.synchronize()
+            results[i] = [o.cpu().numpy() for o in outs]
+        except Exception as e:      # surfaced below
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, (_, _, fr, offs) in enumerate(jobs):
+        exp = np.stack([c_oracle.temporal_median(fr[offs[v]:offs[v + 1]]) for v in range(len(offs) - 1)])
+        for o in results[i]:
+            np.testing.assert_array_equal(o, exp)
