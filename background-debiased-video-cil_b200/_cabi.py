@@ -41,6 +41,7 @@ SIGNATURES = {
     "bgd_temporal_median_varlen_u8_host": (_c.c_int, [_vp, _i64p, _c.c_int64, _c.c_int64, _vp, _c.c_int]),
     "bgd_nan_temporal_reduce_f32": (_c.c_int, [_vp, _c.c_int64, _c.c_int64, _c.c_int, _c.c_int, _vp, _vp, _vp]),
     "bgd_nan_temporal_reduce_varlen_f32": (_c.c_int, [_vp, _i64p, _c.c_int64, _c.c_int64, _c.c_int, _c.c_int, _vp, _vp, _vp]),
+    "bgd_actor_cut_mix_u8": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _vp, _vp, _vp]),
     "bgd_bgmix_blend_f32": (_c.c_int, _blend_common + [_vp]),
     "bgd_bgmix_blend_u8pool_f32": (_c.c_int, _blend_common + [_vp]),
     "bgd_bgmix_blend_normfg_f32": (_c.c_int, [_vp, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64,

@@ -446,6 +446,13 @@ int bgd_nan_temporal_reduce_f32(const float *d_frames, int64_t T, int64_t N, int
                              static_cast<cudaStream_t>(stream));
 }
 
+int bgd_actor_cut_mix_u8(const uint8_t *d_actor, const uint8_t *d_mask, const uint8_t *d_scene, int64_t n, uint8_t *d_out,
+                         uint64_t *d_mask_sum, void *stream)
+{
+    return launch_cutmix(d_actor, d_mask, d_scene, n, d_out, reinterpret_cast<unsigned long long *>(d_mask_sum),
+                         static_cast<cudaStream_t>(stream));
+}
+
 int bgd_nan_temporal_reduce_varlen_f32(const float *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, int avg_method,
                                        int zero_is_missing, uint8_t *d_out_u8, float *d_out_f32, void *stream)
 {

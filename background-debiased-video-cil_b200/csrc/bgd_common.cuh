@@ -61,6 +61,8 @@ int launch_bgmix(const uint8_t *d_fg, const float *d_fg_norm, int64_t B, int64_t
 int launch_sum_f32(const float *d_x, int64_t n, double *d_sum, cudaStream_t stream);
 int launch_nan_reduce(const float *d_frames, int64_t T, int64_t N, int avg_method, int zero_is_missing, uint8_t *d_out_u8,
                       float *d_out_f32, cudaStream_t stream);
+int launch_cutmix(const uint8_t *d_actor, const uint8_t *d_mask, const uint8_t *d_scene, int64_t n, uint8_t *d_out,
+                  unsigned long long *d_mask_sum, cudaStream_t stream);
 int launch_nan_reduce_varlen(const float *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, int avg_method,
                              int zero_is_missing, uint8_t *d_out_u8, float *d_out_f32, cudaStream_t stream);
 

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Sequence
+from typing import Sequence, Tuple
 
 import torch
 
@@ -144,6 +144,30 @@ def nan_temporal_reduce_f32(frames: torch.Tensor, avg_method: int, zero_is_missi
 @nan_temporal_reduce_f32.register_fake
 def _(frames, avg_method, zero_is_missing):
     return frames.new_empty(frames.shape[1:])
+
+
+# --------------------------------------------------------------------------- #
+# ActorCutMix blend (actor_cut_mix_loader.py:143-163)
+# --------------------------------------------------------------------------- #
+@torch.library.custom_op("bgdebias::actor_cut_mix", mutates_args=(), device_types="cuda")
+def actor_cut_mix(actor: torch.Tensor, mask: torch.Tensor, scene: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """uint8 ``[T,H,W,3]`` x3 -> (``actor * mask + scene * (1 - mask)`` uint8, int64 scalar = sum of the mask's channel 0)."""
+    for name, t in (("actor", actor), ("mask", mask), ("scene", scene)):
+        _require(t.dtype == torch.uint8, f"actor_cut_mix: {name} must be uint8")
+    _require(actor.shape == mask.shape == scene.shape, "actor_cut_mix: actor, mask and scene must have one shape")
+    _require(actor.dim() >= 1 and actor.shape[-1] == 3, "actor_cut_mix: channel-last [..., 3] frames expected")
+    actor, mask, scene = actor.contiguous(), mask.contiguous(), scene.contiguous()
+    out = torch.empty_like(actor)
+    total = torch.zeros((), dtype=torch.int64, device=actor.device)
+    with torch.cuda.device(actor.device):
+        _cabi.check(_cabi.lib().bgd_actor_cut_mix_u8(actor.data_ptr(), mask.data_ptr(), scene.data_ptr(), actor.numel(),
+                                                     out.data_ptr(), total.data_ptr(), _stream_ptr(actor.device)))
+    return out, total
+
+
+@actor_cut_mix.register_fake
+def _(actor, mask, scene):
+    return torch.empty_like(actor), actor.new_empty((), dtype=torch.int64)
 
 
 # --------------------------------------------------------------------------- #

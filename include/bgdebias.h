@@ -119,6 +119,16 @@ int bgd_nan_temporal_reduce_varlen_f32(const float *d_frames, const int64_t *h_o
                                        int avg_method, int zero_is_missing, uint8_t *d_out_u8,
                                        float *d_out_f32, void *stream);
 
+/* ---- ActorCutMix blend -----------------------------------------------------------------------
+ * Replaces, for all frames of a clip in one launch,
+ *   actor_cut_mix = actor_img * actor_mask + scene_img * (1 - actor_mask)   libs/loader/actor_cut_mix_loader.py:143-148
+ *   foreground_area += human_mask[:, :, 0].sum()                            :154-163 (_calc_foreground_ratio)
+ * d_actor, d_mask, d_scene, d_out: n uint8 elements each ([T][H][W][3], channel innermost), 16-byte aligned;
+ * numpy's uint8 (wrapping) arithmetic, exact for any mask value.  d_mask_sum (device uint64, may be NULL)
+ * receives the sum of the mask bytes of channel 0 (elements with index % 3 == 0). */
+int bgd_actor_cut_mix_u8(const uint8_t *d_actor, const uint8_t *d_mask, const uint8_t *d_scene, int64_t n,
+                         uint8_t *d_out, uint64_t *d_mask_sum, void *stream);
+
 /* ---- BG-mix blend ------------------------------------------------------------------------
  * Replaces, for a whole batch in one launch,
  *   libs/loader/comix_loader.py:138-145   BackgroundMixDataset._mix_background

@@ -9,6 +9,7 @@ Stubs (nothing else is replaced):
 * ``mmaction.datasets.RawframeDataset`` -- minimal base whose ``prepare_train_frames`` runs a
                                            caller-supplied pipeline callable
 * ``mmaction.datasets.builder.DATASETS``-- ``register_module()`` -> identity decorator
+* ``mmaction.datasets.pipelines.Compose``-- placeholder; the tests replace the dataset's pipelines with callables
 """
 from __future__ import annotations
 
@@ -60,7 +61,11 @@ def _install_stubs() -> None:
         ds.builder = bd
         ds.PIPELINES = bd.PIPELINES
         mm.datasets = ds
-        sys.modules.update({"mmaction": mm, "mmaction.datasets": ds, "mmaction.datasets.builder": bd})
+        pl = types.ModuleType("mmaction.datasets.pipelines")
+        pl.Compose = lambda cfgs: (lambda results: results)      # never called by the tests: pipelines are replaced
+        ds.pipelines = pl
+        sys.modules.update({"mmaction": mm, "mmaction.datasets": ds, "mmaction.datasets.builder": bd,
+                            "mmaction.datasets.pipelines": pl})
 
 
 def _load(name: str, rel: str):
@@ -74,6 +79,11 @@ def _load(name: str, rel: str):
 def load_extract_background():
     """The module at cil_tools/extract_background.py (``bg_extraction_tmf`` :42-75)."""
     return _load("_ref_extract_background", os.path.join("cil_tools", "extract_background.py"))
+
+
+def load_actor_cut_mix_loader():
+    """The module at libs/loader/actor_cut_mix_loader.py (``ActorCutMixDataset.actor_cut_mix`` :135-152)."""
+    return _load("_ref_actor_cut_mix_loader", os.path.join("libs", "loader", "actor_cut_mix_loader.py"))
 
 
 def load_comix_loader():
