@@ -290,6 +290,12 @@ class BackgroundMixDataset(_Base):
             result['bg_idx'], result['bg_top'], result['bg_left'], result['bg_apply'] = bg_idx, top, left, 1
             return result
 
+        if torch.cuda._is_in_bad_fork():
+            raise RuntimeError(
+                "BackgroundMixDataset(device_mix=False) blends on the GPU inside __getitem__, but this DataLoader worker "
+                "was forked after CUDA was initialised and cannot use it.  Use device_mix=True with "
+                "collate_fn=dataset.host_collate and dataset.device_finish(batch) in the training process (workers then "
+                "never touch CUDA), or num_workers=0, or multiprocessing_context='spawn'.  There is no CPU blend.")
         bg_img, bg_idx = self._get_bg_image()
         bg_img = resize_like_reference(bg_img, self.bg_resize)           # Resize(bg_resize), :72
         top, left = draw_crop(bg_img.shape[1], bg_img.shape[2], (th, tw))   # RandomCrop, :73
