@@ -314,7 +314,8 @@ def run_ours(args):
         try:
             from bgdebias_b200.pool import BackgroundPool
             names = [f"r{rank}_v{i:05d}" for i in range(V)]
-            BackgroundPool.all_gather(names[:8], out[:8])                    # warm-up (NCCL channel set-up)
+            all_names, all_bgs = BackgroundPool.all_gather(names, out)       # warm-up at full size (NCCL channels, buffer registration)
+            del all_bgs
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
