@@ -5,7 +5,7 @@
 //
 // Same idea as median_colplane.cuh (one thread owns whole byte columns, so the 8-pass radix
 // select needs no communication), rebuilt around what the instruction-throughput probes
-// (profiles/r1_microbench2.txt) say about B200:
+// (profiles/r1_microbench_instruction_throughput.txt, r1_microbench2_*.txt) say about B200:
 //
 //  * LOP3/SHF/PRMT/SEL share one 64-lane/clk pipe and the column-plane kernel saturates it;
 //    POPC has its own 16-lane/clk pipe and IMAD runs on the FMA pipe, both idle there.
@@ -13,24 +13,27 @@
 //    column in one register -- the shared-memory read and the byte gather the column-plane kernel
 //    spends 0.5 LDS + 0.25 PRMT per byte on become 1/16 instruction per byte.
 //
-// So: a CTA tile is [T rows] x [256 bytes], staged as two 128-byte-wide strips by 2-D TMA tensor
-// copies (boxes of 128 B x 2^k rows, 128-byte swizzle, one mbarrier).  The swizzle (16-byte chunk
-// index ^= row % 8) is what makes the transposing loads bank-conflict free: 122.7 B/clk/SM
-// measured against 32 B/clk/SM for an unswizzled 256-byte pitch.  Two warps share a strip; lane
-// (g = lane / 4, q = lane % 4) owns byte columns 16 chunk(q) + g and + 8 of it for ALL T rows,
-// chunk(q) = {0,4,1,5}[q] for the even warp and {2,6,3,7}[q] for the odd one.  One ldmatrix.x2
-// gives it 8 rows of both; 8 registers (32 rows) of a column are bit-transposed in place (3 stages of masked
-// shifts) into 8 plane words: word b holds bit b of 32 rows.  A column of T rows is NH = ceil(T / 16)
-// half groups: NH / 2 full groups per column plus, when NH is odd, one group that the lane's two
-// columns share (16 rows each; the columns' alive masks keep them apart), so the work follows T in
-// steps of 16 rows.  Per pass b = 7..0 and word:  z = alive & plane_b (LOP3), POPC(z)
-// accumulated by IMAD (neither on the LOP3 pipe), and alive &= plane_b ^ keep (LOP3).  The rank
-// bookkeeping is 4 bitwise operations per column and pass.
+// So: a CTA tile is [T rows] x [128 or 256 bytes], staged as 128-byte-wide strips by 2-D TMA tensor
+// copies (boxes of 128 B x 2^k rows, 128-byte swizzle, one mbarrier per buffer; a ring of 1-4
+// buffers, as many as fit).  The swizzle (16-byte chunk index ^= row % 8) is what makes the
+// transposing loads bank-conflict free: 122.7 B/clk/SM measured against 32 B/clk/SM for an
+// unswizzled 256-byte pitch.  Two warps share a strip; lane (g = lane / 4, q = lane % 4) owns byte
+// columns 16 chunk(q) + g and + 8 of it for ALL T rows, chunk(q) = {0,4,1,5}[q] for the even warp and
+// {2,6,3,7}[q] for the odd one.  One ldmatrix.x2 gives it 8 rows of both; 8 registers (32 rows) of a
+// column are bit-transposed in place (3 stages of masked shifts) into 8 plane words: word b holds
+// bit b of 32 rows.  A column of T rows is NH = ceil(T / 16) half groups: NH / 2 full groups per
+// column plus, when NH is odd, one group that the lane's two columns share (16 rows each; the
+// columns' alive masks keep them apart), so the work follows T in steps of 16 rows.  For
+// 256 < T <= 512 twice the warps read a strip and each lane keeps one of its two columns.
+//  * Per pass b = 7..0 and word:  z = alive & plane_b (LOP3), POPC(z) accumulated by IMAD (neither
+//    on the LOP3 pipe), and alive &= plane_b ^ keep (LOP3).  The select state is one integer per
+//    column, rc = rank - alive count; the result bits accumulate by IMAD.
 //  * Even T: the second rank (T/2) shares the first's state until the pass in which they
 //    disagree; after that it is the minimum of its own alive set (an OR over the words instead of
 //    a count).
-//  * As soon as every lane has its columns in registers the CTA's next tile is requested, so the
-//    TMA copies land while the select runs on registers; several CTAs per SM overlap the rest.
+//  * As soon as every lane has its columns in registers the CTA's next tile is requested (the warps
+//    take turns at it), so the TMA copies land while the select runs on registers; several CTAs per
+//    SM overlap the rest.
 #pragma once
 
 #include "median_colplane.cuh"
