@@ -21,7 +21,8 @@ on its original device.  Works with ``num_workers=0`` or CUDA-capable workers.
 collated uint8 batch into the fp32 training tensor ``[B,T,3,H,W]`` with one kernel launch.  With DataLoader
 worker processes use ``collate_fn=dataset.host_collate`` (host tensors only, safe after ``fork``) and call
 ``dataset.device_finish(batch)`` in the training process: the batch crosses PCIe as uint8, a quarter of the
-reference's fp32 bytes.
+reference's fp32 bytes.  The pipeline may also stop before its last ``Resize((224, 224), keep_ratio=False)``: crops of
+mixed sizes are packed by ``host_collate`` and resized (cv2 INTER_LINEAR, bit for bit) inside the blend launch.
 """
 from __future__ import annotations
 
@@ -328,16 +329,36 @@ class BackgroundMixDataset(_Base):
     # ---- batch API (device_mix=True) -------------------------------------------------------------
     def mix_batch_on_device(self, fg_u8: torch.Tensor, bg_idx, bg_top, bg_left, bg_apply,
                             img_mean: Optional[Sequence[float]] = None, img_std: Optional[Sequence[float]] = None,
-                            layout: str = "NTCHW") -> torch.Tensor:
+                            layout: str = "NTCHW", fg_geom: Optional[torch.Tensor] = None,
+                            fg_frames: Optional[int] = None) -> torch.Tensor:
         """uint8 ``[B,T,H,W,3]`` (host or device) + per-sample draws -> fp32 ``[B,T,3,H,W]`` on the device.
         ``img_mean``/``img_std`` are the foreground's ``Normalize`` parameters (default: the bg ones,
-        as in every shipped config)."""
+        as in every shipped config).
+
+        Clips whose size is not ``bg_crop_size`` -- a pipeline that stops before the final
+        ``Resize((224, 224), keep_ratio=False)`` (config :136) -- are resized inside the same launch with cv2's
+        INTER_LINEAR arithmetic: either a stacked batch of one other size, or packed crops of mixed sizes
+        (``fg_u8`` flat, ``fg_geom`` int64 ``[B,5]``, ``fg_frames`` = T; see ``ops.pack_clips``)."""
         dev = self.device
         pool = self.device_pool()
         mean = self.bg_mean if img_mean is None else img_mean
         std = self.bg_std if img_std is None else img_std
         lut = self._lut(tuple(mean), tuple(std))
         as_dev = lambda v, dt: torch.as_tensor(v, dtype=dt).to(dev, non_blocking=True)   # noqa: E731
+        th, tw = self.bg_crop_size
+        if fg_geom is None and tuple(fg_u8.shape[2:4]) != (th, tw):
+            B, T, h, w, _ = fg_u8.shape
+            frame = h * w * 3
+            fg_geom = torch.tensor([[b * T * frame, h, w, w * 3, frame] for b in range(B)], dtype=torch.int64)
+            flat = fg_u8.reshape(-1)
+            fg_u8 = torch.cat([flat, flat.new_zeros(4 + (-flat.numel()) % 4)])
+            fg_frames = T
+        if fg_geom is not None:
+            return torch.ops.bgdebias.bgmix_resize_blend(
+                fg_u8.to(dev, non_blocking=True), fg_geom, int(fg_frames), th, tw, pool.tensor,
+                pool.rows(as_dev(bg_idx, torch.int32).clamp_(min=0)), as_dev(bg_top, torch.int32), as_dev(bg_left, torch.int32),
+                as_dev(bg_apply, torch.uint8), lut, torch.tensor(self.bg_mean), torch.tensor(self.bg_std), float(self.alpha),
+                layout)
         return torch.ops.bgdebias.bgmix_blend(
             fg_u8.to(dev, non_blocking=True), pool.tensor, pool.rows(as_dev(bg_idx, torch.int32).clamp_(min=0)),
             as_dev(bg_top, torch.int32), as_dev(bg_left, torch.int32), as_dev(bg_apply, torch.uint8), lut,
@@ -355,13 +376,21 @@ class BackgroundMixDataset(_Base):
         the uint8 clips ``[B,T,H,W,3]`` and the per-sample draws into host tensors.  Pair it with
         :meth:`device_finish` in the training process; with ``pin_memory=True`` the batch travels as uint8,
         a quarter of the bytes of the reference's fp32 batch (libs/cil/cil.py:203-210)."""
-        out = {
-            'imgs': torch.stack([torch.as_tensor(s['imgs']) for s in samples]),
+        clips = [torch.as_tensor(s['imgs']) for s in samples]
+        out = {}
+        if all(c.shape == clips[0].shape for c in clips):
+            out['imgs'] = torch.stack(clips)
+        else:
+            # the pipeline stopped before Resize((224, 224), keep_ratio=False) (config :136): MultiScaleCrop's crops differ in
+            # size per sample, so they travel packed and device_finish resizes them inside the blend launch
+            out['imgs'], out['fg_geom'] = ops.pack_clips(clips)
+            out['fg_frames'] = int(clips[0].shape[0])
+        out.update({
             'bg_idx': torch.tensor([int(s['bg_idx']) for s in samples], dtype=torch.int64),
             'bg_top': torch.tensor([int(s['bg_top']) for s in samples], dtype=torch.int32),
             'bg_left': torch.tensor([int(s['bg_left']) for s in samples], dtype=torch.int32),
             'bg_apply': torch.tensor([int(s['bg_apply']) for s in samples], dtype=torch.uint8),
-        }
+        })
         if 'label' in samples[0]:
             out['label'] = torch.stack([torch.as_tensor(s['label']) for s in samples])
         if 'randAug' in samples[0]:
@@ -372,9 +401,10 @@ class BackgroundMixDataset(_Base):
         """The GPU half of the ``device_mix=True`` path: turns a :meth:`host_collate` batch into the dict the
         reference's default_collate would hand the model (``imgs`` fp32 ``[B,T,3,H,W]`` on the device, ``label``,
         ``randAug``, ``bg_idx``) with one fused launch."""
-        out = {k: v for k, v in batch.items() if k not in ('imgs', 'bg_top', 'bg_left', 'bg_apply')}
+        out = {k: v for k, v in batch.items() if k not in ('imgs', 'bg_top', 'bg_left', 'bg_apply', 'fg_geom', 'fg_frames')}
         out['imgs'] = self.mix_batch_on_device(batch['imgs'], batch['bg_idx'], batch['bg_top'], batch['bg_left'],
-                                               batch['bg_apply'], layout=layout)
+                                               batch['bg_apply'], layout=layout, fg_geom=batch.get('fg_geom'),
+                                               fg_frames=batch.get('fg_frames'))
         return out
 
     def gpu_collate(self, samples: List[dict]) -> dict:

@@ -496,6 +496,27 @@ int bgd_bgmix_blend_normfg_f32(const float *d_fg_norm, int64_t B, int64_t T, int
                         d_apply, nullptr, h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int bgd_resize_bilinear_u8(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B, int64_t T, int64_t H,
+                           int64_t W, uint8_t *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    return launch_resize_u8(d_src, src_bytes, h_geom, B, T, H, W, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_bgmix_resize_blend_f32(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B, int64_t T, int64_t H,
+                               int64_t W, const void *d_bg_pool, int pool_is_u8, int64_t P, int64_t Hb, int64_t Wb,
+                               const int32_t *d_bg_idx, const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
+                               const float *d_fg_lut, const float *h_bg_mean, const float *h_bg_std, double alpha, int layout,
+                               float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    return launch_resize_blend(d_src, src_bytes, h_geom, B, T, H, W, d_bg_pool, pool_is_u8 != 0, P, Hb, Wb, d_bg_idx, d_top,
+                               d_left, d_apply, d_fg_lut, h_bg_mean, h_bg_std, alpha, layout, d_out,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t H, int64_t W, const float *d_bg_pool,
                              int64_t P, int64_t Hb, int64_t Wb, const int32_t *h_bg_idx, const int32_t *h_top,
                              const int32_t *h_left, const uint8_t *h_apply, const float *d_fg_lut,

@@ -58,6 +58,13 @@ int launch_bgmix(const uint8_t *d_fg, const float *d_fg_norm, int64_t B, int64_t
                  const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
                  const float *d_lut, const float *h_mean, const float *h_std, double alpha,
                  int layout, float *d_out, cudaStream_t stream);
+int launch_resize_u8(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B, int64_t T, int64_t H, int64_t W,
+                     uint8_t *d_out, cudaStream_t stream);
+int launch_resize_blend(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B, int64_t T, int64_t H,
+                        int64_t W, const void *d_pool, bool pool_is_u8, int64_t P, int64_t Hb, int64_t Wb,
+                        const int32_t *d_bg_idx, const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
+                        const float *d_lut, const float *h_mean, const float *h_std, double alpha, int layout, float *d_out,
+                        cudaStream_t stream);
 int launch_sum_f32(const float *d_x, int64_t n, double *d_sum, cudaStream_t stream);
 int launch_nan_reduce(const float *d_frames, int64_t T, int64_t N, int avg_method, int zero_is_missing, uint8_t *d_out_u8,
                       float *d_out_f32, cudaStream_t stream);

@@ -15,6 +15,10 @@ built library (``ImportError`` otherwise).  Ops are stream-ordered and never syn
                           Tensor apply, Tensor fg_lut, Tensor bg_mean, Tensor bg_std,
                           float alpha, str layout) -> Tensor
         the batched form of BackgroundMixDataset._mix_background (libs/loader/comix_loader.py:138-145).
+    bgdebias::resize_bilinear(Tensor src, Tensor geom, int T, int H, int W) -> Tensor
+    bgdebias::bgmix_resize_blend(Tensor src, Tensor geom, int T, int H, int W, <bgmix_blend arguments>) -> Tensor
+        the pipeline's Resize((W, H), keep_ratio=False) (config ..._bgmix_plus_randAug.py:136; cv2 INTER_LINEAR, bit-exact)
+        on packed uint8 crops, alone or fused with the blend.
 """
 from __future__ import annotations
 
@@ -215,6 +219,92 @@ def _(fg, bg_pool, bg_idx, top, left, apply, fg_lut, bg_mean, bg_std, alpha, lay
     B, T, H, W, _ = fg.shape
     shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
     return fg.new_empty(shape, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------- #
+# foreground pipeline tail: Resize (cv2 INTER_LINEAR, bit-exact) [-> Normalize -> FormatShape -> blend]
+# --------------------------------------------------------------------------- #
+def pack_clips(clips, pin: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Host helper: uint8 clips ``[T, h_i, w_i, 3]`` of different crop sizes -> (flat uint8 buffer, int64 ``[B, 5]`` geometry
+    ``{offset, h, w, row stride, frame stride}``) in the form ``resize_bilinear`` / ``bgmix_resize_blend`` take.  Pure CPU."""
+    clips = [torch.as_tensor(c) for c in clips]
+    T = clips[0].shape[0] if clips else 0
+    geom = torch.empty((len(clips), 5), dtype=torch.int64)
+    total = 0
+    for i, c in enumerate(clips):
+        _require(c.dtype == torch.uint8 and c.dim() == 4 and c.shape[3] == 3, "pack_clips: clips must be uint8 [T, h, w, 3]")
+        _require(c.shape[0] == T, "pack_clips: every clip needs the same number of frames")
+        h, w = int(c.shape[1]), int(c.shape[2])
+        geom[i] = torch.tensor([total, h, w, w * 3, h * w * 3])
+        total += T * h * w * 3
+    size = total + 4 + (-total) % 4                       # 32-bit loads: multiple of 4, slack for one-column crops
+    buf = torch.zeros(size, dtype=torch.uint8, pin_memory=pin)
+    for i, c in enumerate(clips):
+        o = int(geom[i, 0])
+        buf[o:o + c.numel()] = c.reshape(-1)
+    return buf, geom
+
+
+def _check_packed(name: str, src: torch.Tensor, geom: torch.Tensor):
+    _require(src.dtype == torch.uint8 and src.dim() == 1, f"{name}: src must be a flat uint8 buffer")
+    _require(geom.dim() == 2 and geom.shape[1] == 5, f"{name}: geom must be int64 [B, 5]")
+    _require(src.numel() % 4 == 0, f"{name}: src must be a multiple of 4 bytes long (ops.pack_clips pads)")
+    g = geom.detach().to("cpu", torch.int64).contiguous()
+    return src.contiguous(), g, ctypes.cast(g.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+
+
+@torch.library.custom_op("bgdebias::resize_bilinear", mutates_args=(), device_types="cuda")
+def resize_bilinear(src: torch.Tensor, geom: torch.Tensor, T: int, H: int, W: int) -> torch.Tensor:
+    """Packed uint8 crops (see :func:`pack_clips`) -> uint8 ``[B, T, H, W, 3]``; every frame equals
+    ``cv2.resize(frame, (W, H), interpolation=cv2.INTER_LINEAR)``, the arithmetic of mmaction's ``Resize``."""
+    src, g, gptr = _check_packed("resize_bilinear", src, geom)
+    out = torch.empty((g.shape[0], T, H, W, 3), dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        _cabi.check(_cabi.lib().bgd_resize_bilinear_u8(src.data_ptr(), src.numel(), gptr, g.shape[0], T, H, W, out.data_ptr(),
+                                                       _stream_ptr(src.device)))
+    return out
+
+
+@resize_bilinear.register_fake
+def _(src, geom, T, H, W):
+    return src.new_empty((geom.shape[0], T, H, W, 3))
+
+
+@torch.library.custom_op("bgdebias::bgmix_resize_blend", mutates_args=(), device_types="cuda")
+def bgmix_resize_blend(src: torch.Tensor, geom: torch.Tensor, T: int, H: int, W: int, bg_pool: torch.Tensor,
+                       bg_idx: torch.Tensor, top: torch.Tensor, left: torch.Tensor, apply: torch.Tensor, fg_lut: torch.Tensor,
+                       bg_mean: torch.Tensor, bg_std: torch.Tensor, alpha: float, layout: str) -> torch.Tensor:
+    """``bgmix_blend(resize_bilinear(src, geom, T, H, W), ...)`` in one launch (the resized uint8 batch never exists)."""
+    src, g, gptr = _check_packed("bgmix_resize_blend", src, geom)
+    B = g.shape[0]
+    _require(bg_pool.dim() == 4 and bg_pool.shape[1] == 3 and bg_pool.dtype in (torch.float32, torch.uint8),
+             "bgmix_resize_blend: bg_pool must be float32 or uint8 [P, 3, Hb, Wb]")
+    _require(layout in _cabi.LAYOUTS, f"bgmix_resize_blend: layout must be one of {sorted(_cabi.LAYOUTS)}")
+    P, _, Hb, Wb = bg_pool.shape
+    dev = src.device
+    for name, t, dt in (("bg_idx", bg_idx, torch.int32), ("top", top, torch.int32), ("left", left, torch.int32),
+                        ("apply", apply, torch.uint8)):
+        _require(t.dtype == dt and t.dim() == 1 and t.shape[0] == B and t.device == dev,
+                 f"bgmix_resize_blend: {name} must be {dt} [B] on {dev}")
+    _require(fg_lut.dtype == torch.float32 and tuple(fg_lut.shape) == (3, 256) and fg_lut.device == dev,
+             "bgmix_resize_blend: fg_lut must be float32 [3, 256] on the device")
+    _require(bg_pool.device == dev, "bgmix_resize_blend: bg_pool must be on the same device as src")
+    bg_pool = bg_pool.contiguous()
+    bg_idx, top, left, apply, fg_lut = (x.contiguous() for x in (bg_idx, top, left, apply, fg_lut))
+    shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().bgd_bgmix_resize_blend_f32(
+            src.data_ptr(), src.numel(), gptr, B, T, H, W, bg_pool.data_ptr(), int(bg_pool.dtype == torch.uint8), P, Hb, Wb,
+            bg_idx.data_ptr(), top.data_ptr(), left.data_ptr(), apply.data_ptr(), fg_lut.data_ptr(), _host3(bg_mean, "bg_mean"),
+            _host3(bg_std, "bg_std"), float(alpha), _cabi.LAYOUTS[layout], out.data_ptr(), _stream_ptr(dev)))
+    return out
+
+
+@bgmix_resize_blend.register_fake
+def _(src, geom, T, H, W, bg_pool, bg_idx, top, left, apply, fg_lut, bg_mean, bg_std, alpha, layout):
+    B = geom.shape[0]
+    return src.new_empty((B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W), dtype=torch.float32)
 
 
 # --------------------------------------------------------------------------- #

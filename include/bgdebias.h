@@ -189,6 +189,33 @@ int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t 
                              const float *h_bg_std, double alpha, int layout, float *d_out,
                              double *h_checksum, int device);
 
+/* ---- foreground pipeline tail: Resize -> Normalize -> FormatShape (-> blend) -----------------
+ * Replaces the tail of the reference's training pipeline
+ *   dict(type='Resize', scale=(224, 224), keep_ratio=False), Normalize, FormatShape('NCHW')
+ *   configs/ucf101/bgmix_plus_randAug/bgmix_seed_1000_inc_10_stages_bgmix_plus_randAug.py:136-138
+ * so that the DataLoader can ship the uint8 crops MultiScaleCrop (:129-135) produces.  Resize is mmaction2 0.x ->
+ * mmcv.imresize -> cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR) (third-party, not in the reference tree);
+ * results are bit-equal to cv2.resize for uint8 RGB images.
+ *
+ *   d_src     packed uint8 source pixels, 4-byte aligned, src_bytes a multiple of 4
+ *   h_geom    HOST int64 [B][5]: {byte offset of the clip's first crop pixel in d_src, crop height, crop width,
+ *             row stride in bytes, frame stride in bytes}; a clip is T frames, pixels RGB interleaved.  A crop of one
+ *             column needs 3 readable bytes after each row (the kernel reads pixel pairs).
+ *   d_out     uint8 [B][T][H][W][3]
+ */
+int bgd_resize_bilinear_u8(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B,
+                           int64_t T, int64_t H, int64_t W, uint8_t *d_out, void *stream);
+
+/* Resize + the blend of bgd_bgmix_blend_f32 in one launch: the [B][T][H][W][3] uint8 intermediate never exists.
+ * Source arguments as bgd_resize_bilinear_u8, blend arguments and arithmetic as bgd_bgmix_blend_f32;
+ * d_bg_pool is fp32 (pool_is_u8 == 0) or uint8 (pool_is_u8 != 0) [P][3][Hb][Wb]. */
+int bgd_bgmix_resize_blend_f32(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B,
+                               int64_t T, int64_t H, int64_t W, const void *d_bg_pool, int pool_is_u8,
+                               int64_t P, int64_t Hb, int64_t Wb, const int32_t *d_bg_idx,
+                               const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply,
+                               const float *d_fg_lut, const float *h_bg_mean, const float *h_bg_std,
+                               double alpha, int layout, float *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
