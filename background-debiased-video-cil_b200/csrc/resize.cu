@@ -17,30 +17,46 @@
 // plus a per-clip table (byte offset of the crop's first pixel, crop height/width, row and frame strides), so a crop can also
 // be addressed inside a full decoded frame without a host-side copy.
 //
-// One thread owns one output pixel of one clip: coefficients and tap addresses are computed once and reused for the T frames
-// of the clip.  Per frame it reads the two 6-byte tap pairs (RGB of two adjacent source pixels) with aligned 32-bit loads and
-// a funnel shift, so neighbouring lanes share cache lines; the 3 results go through the normalisation table and the blend of
-// bgmix.cu and are stored as one coalesced 128-byte row per warp and channel plane.
+// The coefficients depend on (source size, destination size, index) only: the host evaluates them once per distinct size
+// (float/double arithmetic exactly as above) into small tables that travel with the per-clip table.  A CTA owns a 32x8 tile of
+// output pixels of one clip, one thread per pixel: it reads its column entry and its row entry, then walks the T frames of the
+// clip.  Per frame it reads the two 6-byte tap pairs (RGB of two adjacent source pixels) with aligned 32-bit loads and a
+// funnel shift, so neighbouring lanes share cache lines, pairs left/right bytes with byte permutes and multiplies with dp2a;
+// the 3 results go through the normalisation table and the blend of bgmix.cu and are stored as one coalesced 128-byte row
+// per warp and channel plane.
 #include "bgd_common.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace bgd {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kTileW = 32, kTileH = 8, kThreads = kTileW * kTileH;
+#ifndef BGD_RESIZE_UNROLL
+#define BGD_RESIZE_UNROLL 1
+#endif
+#ifndef BGD_RESIZE_MINBLOCKS
+#define BGD_RESIZE_MINBLOCKS 8
+#endif
+constexpr int kFrameUnroll = BGD_RESIZE_UNROLL, kBlendMinBlocks = BGD_RESIZE_MINBLOCKS;
+
+struct Coef {                  // one per destination column / row, built on the host
+    int32_t i0, i1;            // columns: byte offset of the left tap in its row, -;  rows: the two source rows (clamped)
+    int32_t c0, c1;            // 11-bit weights of the two taps
+};
 
 struct ClipGeom {              // one per clip, built on the host
     int64_t offset;            // bytes from d_src to the crop's first pixel of frame 0
     int64_t row_stride, frame_stride;
-    double scale_x, scale_y;
-    int32_t h, w;
+    int32_t xtab, ytab;        // first entry of the clip's column / row coefficients in the Coef array
 };
 
 struct TailParams {
     const uint8_t *src;
     const ClipGeom *geom;
+    const Coef *coef;
     // blend half (unused by the uint8 resize kernel)
     const void *pool;
     const int32_t *bg_idx, *top, *left;
@@ -57,37 +73,18 @@ struct TailParams {
 struct Taps {
     int64_t row0, row1;        // byte offsets (from src) of the left tap in the two source rows, frame 0
     uint32_t a01;              // column weights, a0 | a1 << 16
-    int32_t b0, b1;            // row weights
+    uint32_t b0, b1;           // row weights
 };
 
-// coefficient of OpenCV's linear resize: destination index d of `dst` over a source of `src` samples
-__device__ __forceinline__ void linear_coeff(int d, int src, double scale, bool clamp, int &s, int &c0, int &c1)
+__device__ __forceinline__ Taps make_taps(const TailParams &prm, const ClipGeom &g, int x, int y)
 {
-    const double pos = __dadd_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), -0.5);
-    float f = __double2float_rn(pos);
-    s = (int)floorf(f);
-    f = __fsub_rn(f, (float)s);
-    if (clamp) {
-        if (s < 0) { s = 0; f = 0.f; }
-        if (s >= src - 1) { s = src - 1; f = 0.f; }
-    }
-    // saturate_cast<short>(c * 2048): 0 <= c <= 1, so no saturation happens
-    c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
-    c1 = __float2int_rn(__fmul_rn(f, 2048.f));
-}
-
-__device__ __forceinline__ Taps make_taps(const ClipGeom &g, int x, int y)
-{
+    const int4 cx = __ldg(reinterpret_cast<const int4 *>(prm.coef + g.xtab + x));
+    const int4 cy = __ldg(reinterpret_cast<const int4 *>(prm.coef + g.ytab + y));
     Taps t;
-    int sx, sy, a0, a1;
-    linear_coeff(x, g.w, g.scale_x, true, sx, a0, a1);
-    linear_coeff(y, g.h, g.scale_y, false, sy, t.b0, t.b1);
-    // the right tap of the last column has weight 0: read the pair one pixel to the left and swap the weights
-    if (sx >= g.w - 1 && g.w >= 2) { sx = g.w - 2; a1 = a0; a0 = 0; }
-    t.a01 = (uint32_t)a0 | ((uint32_t)a1 << 16);
-    const int y0 = max(0, min(sy, g.h - 1)), y1 = max(0, min(sy + 1, g.h - 1));
-    t.row0 = g.offset + (int64_t)y0 * g.row_stride + (int64_t)sx * 3;
-    t.row1 = g.offset + (int64_t)y1 * g.row_stride + (int64_t)sx * 3;
+    t.a01 = (uint32_t)cx.z | ((uint32_t)cx.w << 16);
+    t.b0 = (uint32_t)cy.z; t.b1 = (uint32_t)cy.w;
+    t.row0 = g.offset + (int64_t)cy.x * g.row_stride + cx.x;
+    t.row1 = g.offset + (int64_t)cy.y * g.row_stride + cx.x;
     return t;
 }
 
@@ -112,7 +109,7 @@ __device__ __forceinline__ void hpass(const uint32_t *w, uint32_t sh, uint32_t a
 // (weights sum to at most 2049/2048 and every shift truncates).  The +2 rides on the first product as 2 << 16.
 __device__ __forceinline__ uint32_t vpass(uint32_t h0, uint32_t h1, const Taps &t)
 {
-    const uint32_t v = (((uint32_t)t.b0 * (h0 >> 4) + 0x20000u) >> 16) + (((uint32_t)t.b1 * (h1 >> 4)) >> 16);
+    const uint32_t v = ((t.b0 * (h0 >> 4) + 0x20000u) >> 16) + ((t.b1 * (h1 >> 4)) >> 16);
     return v >> 2;
 }
 
@@ -127,7 +124,7 @@ __device__ __forceinline__ void for_each_frame(const TailParams &prm, const Clip
         const uint32_t *w0 = base + (t.row0 >> 2), *w1 = base + (t.row1 >> 2);
         const uint32_t s0 = ((uint32_t)t.row0 & 3u) * 8u, s1 = ((uint32_t)t.row1 & 3u) * 8u;
         const int64_t step = g.frame_stride >> 2;
-#pragma unroll 2
+#pragma unroll kFrameUnroll
         for (int64_t f = 0; f < prm.T; ++f, w0 += step, w1 += step) {
             uint32_t h0[3], h1[3];
             hpass(w0, s0, t.a01, h0);
@@ -149,51 +146,50 @@ __device__ __forceinline__ void for_each_frame(const TailParams &prm, const Clip
 
 __global__ void __launch_bounds__(kThreads) resize_u8_kernel(const TailParams prm)
 {
-    const int64_t b = blockIdx.y;
-    const int64_t HW = prm.H * prm.W;
-    const uint32_t p = blockIdx.x * kThreads + threadIdx.x;
-    if (p >= HW) return;
+    const int64_t b = blockIdx.z;
+    const int x = blockIdx.x * kTileW + threadIdx.x, y = blockIdx.y * kTileH + threadIdx.y;
+    if (x >= prm.W || y >= prm.H) return;
     const ClipGeom g = prm.geom[b];
-    const int y = (int)(p / (uint32_t)prm.W), x = (int)(p - (uint32_t)y * (uint32_t)prm.W);
-    const Taps t = make_taps(g, x, y);
-    uint8_t *out = prm.out_u8 + (b * prm.T * HW + p) * 3;
-    const int64_t frame = HW * 3;
+    const Taps t = make_taps(prm, g, x, y);
+    const int64_t HW = prm.H * prm.W, frame = HW * 3;
+    uint8_t *out = prm.out_u8 + (b * prm.T * HW + (int64_t)y * prm.W + x) * 3;
     auto emit = [&](int64_t f, int c, uint32_t v) { out[f * frame + c] = (uint8_t)v; };
     if ((g.frame_stride & 3) == 0) for_each_frame<true>(prm, g, t, emit);
     else                           for_each_frame<false>(prm, g, t, emit);
 }
 
 template <typename PoolT>
-__global__ void __launch_bounds__(kThreads, 4) resize_blend_kernel(const TailParams prm)
+__global__ void __launch_bounds__(kThreads, kBlendMinBlocks) resize_blend_kernel(const TailParams prm)
 {
     __shared__ float s_lut[3 * 256];
-    for (int i = threadIdx.x; i < 3 * 256; i += kThreads) s_lut[i] = __ldg(prm.lut + i);
+    for (int i = threadIdx.y * kTileW + threadIdx.x; i < 3 * 256; i += kThreads) s_lut[i] = __ldg(prm.lut + i);
     __syncthreads();
 
-    const int64_t b = blockIdx.y;
-    const int64_t HW = prm.H * prm.W;
-    const uint32_t p = blockIdx.x * kThreads + threadIdx.x;
-    if (p >= HW) return;
+    const int64_t b = blockIdx.z;
+    const int x = blockIdx.x * kTileW + threadIdx.x, y = blockIdx.y * kTileH + threadIdx.y;
+    if (x >= prm.W || y >= prm.H) return;
     const ClipGeom g = prm.geom[b];
-    const int y = (int)(p / (uint32_t)prm.W), x = (int)(p - (uint32_t)y * (uint32_t)prm.W);
-    const Taps t = make_taps(g, x, y);
+    const Taps t = make_taps(prm, g, x, y);
 
     const bool apply = prm.apply[b] != 0;
     float bgw[3] = {0.f, 0.f, 0.f};                  // normalised background * alpha
     if (apply) {
+        // one pool image has fewer than 2^31 elements (checked on the host): only the image index needs 64 bits
+        const int Hb = (int)prm.Hb, Wb = (int)prm.Wb, plane = Hb * Wb;
         int64_t idx = prm.bg_idx[b];
         idx = idx < 0 ? 0 : (idx >= prm.P ? prm.P - 1 : idx);               // host validates; clamp = no OOB
-        const int64_t top = min(max((int64_t)prm.top[b], (int64_t)0), prm.Hb - prm.H);
-        const int64_t left = min(max((int64_t)prm.left[b], (int64_t)0), prm.Wb - prm.W);
-        const PoolT *pb = static_cast<const PoolT *>(prm.pool) + ((idx * 3) * prm.Hb + (top + y)) * prm.Wb + left + x;
+        const int top = min(max(prm.top[b], 0), Hb - (int)prm.H);
+        const int left = min(max(prm.left[b], 0), Wb - (int)prm.W);
+        const PoolT *pb = static_cast<const PoolT *>(prm.pool) + idx * (3 * plane) + ((top + y) * Wb + left + x);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float raw = (float)__ldg(pb + (int64_t)c * prm.Hb * prm.Wb);
+            const float raw = (float)__ldg(pb + c * plane);
             bgw[c] = __fmul_rn(__fdiv_rn(__fsub_rn(raw, prm.mean[c]), prm.std[c]), prm.w_bg);
         }
     }
 
-    float *out = prm.out + b * prm.T * 3 * HW + p;
+    const int64_t HW = prm.H * prm.W;
+    float *out = prm.out + b * prm.T * 3 * HW + (int64_t)y * prm.W + x;
     const int64_t st = prm.out_stride_t, sc = prm.out_stride_c;
     const float w_fg = prm.w_fg;
     auto emit = [&](int64_t f, int c, uint32_t v) {
@@ -204,12 +200,57 @@ __global__ void __launch_bounds__(kThreads, 4) resize_blend_kernel(const TailPar
     else                           for_each_frame<false>(prm, g, t, emit);
 }
 
-// Validates the host geometry table [B][5] = {offset, h, w, row stride, frame stride} against the buffer and uploads it.
-int upload_geom(const int64_t *h_geom, int64_t B, int64_t T, int64_t H, int64_t W, int64_t src_bytes, Workspace &ws,
-                cudaStream_t stream)
+// ---- host: coefficient tables ------------------------------------------------------------------------------------------------
+// cv::resize (INTER_LINEAR, 8-bit): inv_scale = dst / src, scale = 1 / inv_scale (doubles); per destination index d:
+// f = float((d + 0.5) * scale - 0.5), s = floor(f), f -= s.  Columns snap taps outside the image onto the border pixel with
+// weights (1, 0); rows keep their fraction and clamp the two tap rows.  Weights: saturate_cast<short>(c * 2048), i.e. the
+// float product (exact, a power of two) rounded half to even.  volatile keeps the compiler from fusing or reassociating.
+void fill_coefs(int src, int dst, bool columns, Coef *out)
 {
-    if (int rc = ws.acquire((size_t)B * sizeof(ClipGeom))) return rc;
-    ClipGeom *hg = static_cast<ClipGeom *>(ws.h_pinned);
+    const volatile double inv_scale = (double)dst / (double)src;
+    const volatile double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dst; ++d) {
+        const volatile double scaled = ((double)d + 0.5) * scale;
+        volatile float f = (float)(scaled - 0.5);
+        int s = (int)std::floor(f);
+        f = f - (float)s;
+        Coef c;
+        if (columns) {
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= src - 1) { s = src - 1; f = 0.f; }
+        }
+        const volatile float one_minus = 1.f - f;
+        c.c0 = (int32_t)std::nearbyint(one_minus * 2048.f);
+        c.c1 = (int32_t)std::nearbyint(f * 2048.f);
+        if (columns) {
+            // the right tap of the last column has weight 0: read the pair one pixel to the left and swap the weights
+            if (s >= src - 1 && src >= 2) { s = src - 2; c.c1 = c.c0; c.c0 = 0; }
+            c.i0 = s * 3; c.i1 = 0;
+        } else {
+            c.i0 = std::max(0, std::min(s, src - 1));
+            c.i1 = std::max(0, std::min(s + 1, src - 1));
+        }
+        out[d] = c;
+    }
+}
+
+struct TableKey { int64_t src; bool columns; int32_t at; };
+
+// Validates the host geometry table [B][5] = {offset, h, w, row stride, frame stride} against the buffer, builds the
+// coefficient tables (one per distinct source size and axis) and uploads both: [ClipGeom x B][Coef x n].
+int upload_geom(const int64_t *h_geom, int64_t B, int64_t T, int64_t H, int64_t W, int64_t src_bytes, Workspace &ws,
+                TailParams *prm, cudaStream_t stream)
+{
+    std::vector<TableKey> tables;
+    std::vector<int32_t> xt(B), yt(B);
+    int64_t n_coef = 0;
+    auto table_of = [&](int64_t src, bool columns) {
+        for (const TableKey &k : tables)
+            if (k.src == src && k.columns == columns) return k.at;
+        tables.push_back({src, columns, (int32_t)n_coef});
+        n_coef += columns ? W : H;
+        return tables.back().at;
+    };
     for (int64_t b = 0; b < B; ++b) {
         const int64_t *q = h_geom + b * 5;
         const int64_t off = q[0], h = q[1], w = q[2], rs = q[3], fs = q[4];
@@ -222,12 +263,23 @@ int upload_geom(const int64_t *h_geom, int64_t B, int64_t T, int64_t H, int64_t 
         if (end > src_bytes)
             return fail(BGD_ERR_INVALID, "resize: clip %lld ends at byte %lld of a %lld-byte buffer", (long long)b,
                         (long long)end, (long long)src_bytes);
-        hg[b].offset = off; hg[b].row_stride = rs; hg[b].frame_stride = fs;
-        hg[b].h = (int32_t)h; hg[b].w = (int32_t)w;
-        hg[b].scale_x = 1.0 / ((double)W / (double)w);        // cv::resize: inv_scale = dsize / ssize; scale = 1 / inv_scale
-        hg[b].scale_y = 1.0 / ((double)H / (double)h);
+        if (n_coef + H + W > INT32_MAX) return fail(BGD_ERR_INVALID, "resize: too many distinct clip sizes");
+        xt[b] = table_of(w, true);
+        yt[b] = table_of(h, false);
     }
-    BGD_CUDA_TRY(cudaMemcpyAsync(ws.d_ptr, ws.h_pinned, (size_t)B * sizeof(ClipGeom), cudaMemcpyHostToDevice, stream));
+    const size_t geom_bytes = (size_t)B * sizeof(ClipGeom), bytes = geom_bytes + (size_t)n_coef * sizeof(Coef);
+    if (int rc = ws.acquire(bytes)) return rc;
+    ClipGeom *hg = static_cast<ClipGeom *>(ws.h_pinned);
+    Coef *hc = reinterpret_cast<Coef *>(static_cast<char *>(ws.h_pinned) + geom_bytes);
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t *q = h_geom + b * 5;
+        hg[b].offset = q[0]; hg[b].row_stride = q[3]; hg[b].frame_stride = q[4];
+        hg[b].xtab = xt[b]; hg[b].ytab = yt[b];
+    }
+    for (const TableKey &k : tables) fill_coefs((int)k.src, (int)(k.columns ? W : H), k.columns, hc + k.at);
+    BGD_CUDA_TRY(cudaMemcpyAsync(ws.d_ptr, ws.h_pinned, bytes, cudaMemcpyHostToDevice, stream));
+    prm->geom = static_cast<const ClipGeom *>(ws.d_ptr);
+    prm->coef = reinterpret_cast<const Coef *>(static_cast<const char *>(ws.d_ptr) + geom_bytes);
     return BGD_OK;
 }
 
@@ -240,8 +292,13 @@ int check_common(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom,
         return fail(BGD_ERR_INVALID, "resize: the source buffer must be 4-byte aligned and a multiple of 4 bytes long "
                                      "(it is read with aligned 32-bit loads)");
     if (B > 65535) return fail(BGD_ERR_INVALID, "resize: batch larger than 65535");
-    if (H * W > INT32_MAX) return fail(BGD_ERR_INVALID, "resize: output size too large");
+    if (H > 65535 * kTileH || W > INT32_MAX / 4) return fail(BGD_ERR_INVALID, "resize: output size too large");
     return BGD_OK;
+}
+
+dim3 tile_grid(int64_t B, int64_t H, int64_t W)
+{
+    return dim3((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kTileH - 1) / kTileH), (unsigned)B);
 }
 
 }  // namespace
@@ -253,12 +310,11 @@ int launch_resize_u8(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_g
     if (B == 0 || T == 0 || H == 0 || W == 0) return BGD_OK;
     if (!d_out) return fail(BGD_ERR_INVALID, "resize: null output");
     Workspace &ws = thread_workspace();
-    if (int rc = upload_geom(h_geom, B, T, H, W, src_bytes, ws, stream)) return rc;
     TailParams prm{};
-    prm.src = d_src; prm.geom = static_cast<const ClipGeom *>(ws.d_ptr); prm.out_u8 = d_out;
+    if (int rc = upload_geom(h_geom, B, T, H, W, src_bytes, ws, &prm, stream)) return rc;
+    prm.src = d_src; prm.out_u8 = d_out;
     prm.T = T; prm.H = H; prm.W = W;
-    const dim3 grid((unsigned)((H * W + kThreads - 1) / kThreads), (unsigned)B);
-    resize_u8_kernel<<<grid, kThreads, 0, stream>>>(prm);
+    resize_u8_kernel<<<tile_grid(B, H, W), dim3(kTileW, kTileH), 0, stream>>>(prm);
     count_launch();
     cudaError_t e = cudaGetLastError();
     const int rc = e == cudaSuccess ? BGD_OK : fail(BGD_ERR_CUDA, "resize_u8_kernel launch failed: %s", cudaGetErrorString(e));
@@ -280,12 +336,14 @@ int launch_resize_blend(const uint8_t *d_src, int64_t src_bytes, const int64_t *
     if (P > 0 && (Hb < H || Wb < W))
         return fail(BGD_ERR_INVALID, "bgmix_resize: crop %lldx%lld larger than pool image %lldx%lld", (long long)H, (long long)W,
                     (long long)Hb, (long long)Wb);
+    if (P > 0 && (Hb > INT32_MAX / 4 || Wb > INT32_MAX / 4 || 3 * Hb * Wb > INT32_MAX))
+        return fail(BGD_ERR_INVALID, "bgmix_resize: pool images larger than 2^31 elements");
     if (layout != BGD_LAYOUT_NTCHW && layout != BGD_LAYOUT_NCTHW) return fail(BGD_ERR_INVALID, "bgmix_resize: unknown layout %d", layout);
 
     Workspace &ws = thread_workspace();
-    if (int rc = upload_geom(h_geom, B, T, H, W, src_bytes, ws, stream)) return rc;
     TailParams prm{};
-    prm.src = d_src; prm.geom = static_cast<const ClipGeom *>(ws.d_ptr);
+    if (int rc = upload_geom(h_geom, B, T, H, W, src_bytes, ws, &prm, stream)) return rc;
+    prm.src = d_src;
     prm.pool = d_pool; prm.bg_idx = d_bg_idx; prm.top = d_top; prm.left = d_left; prm.apply = d_apply; prm.lut = d_lut;
     prm.out = d_out;
     prm.T = T; prm.H = H; prm.W = W; prm.P = P > 0 ? P : 1; prm.Hb = Hb; prm.Wb = Wb;
@@ -295,9 +353,8 @@ int launch_resize_blend(const uint8_t *d_src, int64_t src_bytes, const int64_t *
     const int64_t HW = H * W;
     if (layout == BGD_LAYOUT_NTCHW) { prm.out_stride_t = 3 * HW; prm.out_stride_c = HW; }
     else                            { prm.out_stride_t = HW;     prm.out_stride_c = T * HW; }
-    const dim3 grid((unsigned)((HW + kThreads - 1) / kThreads), (unsigned)B);
-    if (pool_is_u8) resize_blend_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(prm);
-    else            resize_blend_kernel<float><<<grid, kThreads, 0, stream>>>(prm);
+    if (pool_is_u8) resize_blend_kernel<uint8_t><<<tile_grid(B, H, W), dim3(kTileW, kTileH), 0, stream>>>(prm);
+    else            resize_blend_kernel<float><<<tile_grid(B, H, W), dim3(kTileW, kTileH), 0, stream>>>(prm);
     count_launch();
     cudaError_t e = cudaGetLastError();
     const int rc = e == cudaSuccess ? BGD_OK : fail(BGD_ERR_CUDA, "resize_blend_kernel launch failed: %s", cudaGetErrorString(e));

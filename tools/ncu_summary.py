@@ -1,10 +1,11 @@
 """Summarise an .ncu-rep (raw + source pages) for one kernel: key metrics, opcode mix, stall mix.
-usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [--segments]"""
+usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [--segments] [--index K]   (K = which captured launch, default 0)"""
 import csv, collections, subprocess, sys, io
 rep = sys.argv[1]
+K = int(sys.argv[sys.argv.index("--index") + 1]) if "--index" in sys.argv else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + K]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "launch__block_size", "launch__grid_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__occupancy_limit_warps", "launch__shared_mem_per_block_dynamic",
@@ -23,7 +24,10 @@ for v, h in sorted(st, reverse=True)[:8]:
     print(f"   {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {v:6.2f}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+per = max(1, (len(starts) - 1) // max(1, len(list(csv.reader(io.StringIO(raw)))) - 2))   # sections per launch (SASS, source)
+rows = rows[starts[per * K]:starts[per * K + 1]]          # the SASS section of launch K
+hdr, data = rows[1], [r for r in rows[2:] if len(r) > 5]
 isrc, iex, ismp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 tot = sum(int(r[iex]) for r in data)
 print(f"-- opcode mix: {tot} warp-instr, {len(data)} SASS lines --")
