@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <unordered_map>
 #include <vector>
 
 namespace bgd {
@@ -242,12 +243,14 @@ int upload_geom(const int64_t *h_geom, int64_t B, int64_t T, int64_t H, int64_t 
                 TailParams *prm, cudaStream_t stream)
 {
     std::vector<TableKey> tables;
+    std::unordered_map<int64_t, int32_t> index;            // 2 * source size + axis -> first entry
     std::vector<int32_t> xt(B), yt(B);
     int64_t n_coef = 0;
     auto table_of = [&](int64_t src, bool columns) {
-        for (const TableKey &k : tables)
-            if (k.src == src && k.columns == columns) return k.at;
+        auto it = index.find(2 * src + (columns ? 1 : 0));
+        if (it != index.end()) return it->second;
         tables.push_back({src, columns, (int32_t)n_coef});
+        index.emplace(2 * src + (columns ? 1 : 0), (int32_t)n_coef);
         n_coef += columns ? W : H;
         return tables.back().at;
     };
