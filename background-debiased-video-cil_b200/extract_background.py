@@ -22,8 +22,10 @@ from __future__ import annotations
 
 import argparse
 import json
+import os
 import pathlib
 import sys
+import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import List
@@ -50,7 +52,7 @@ def parse_args(argv=None):
     parser.add_argument('--method', default='tmf')
     parser.add_argument('--avg_method', default='median')
     # extensions
-    parser.add_argument('--decode_threads', type=int, default=4)
+    parser.add_argument('--decode_threads', type=int, default=0, help='host decoder threads per shard; 0 = the host cores divided by the shards')
     parser.add_argument('--slab_mb', type=int, default=512)
     return parser.parse_args(argv)
 
@@ -82,6 +84,45 @@ def read_frames(data_path: pathlib.Path, from_video: bool, interval: int, max_fr
                     frames.append(img)
             count += 1
     return frames
+
+
+_scratch = threading.local()
+
+
+def read_frames_packed(data_path: pathlib.Path, from_video: bool, interval: int, max_frames: int) -> np.ndarray:
+    """:func:`read_frames` for the batched path: the same frames as one ``[T, H, W, 3]`` uint8 array that lives in a
+    scratch buffer of the calling thread (valid until the thread's next call).  The decoder writes each kept frame
+    straight into the scratch, so a decoder thread allocates nothing per frame."""
+    if not from_video:
+        frames = read_frames(data_path, from_video, interval, max_frames)
+        return np.stack(frames) if frames else np.empty((0,), np.uint8)
+    cap = cv2.VideoCapture(str(data_path))
+    n, count, buf = 0, 0, getattr(_scratch, "buf", None)
+    try:
+        while cap.isOpened() and n <= max_frames:
+            keep = count % interval == 0
+            if not keep:
+                if not cap.grab():                                 # skipped position: advance without converting
+                    break
+                count += 1
+                continue
+            dst = buf[n] if (buf is not None and n < len(buf)) else None
+            ret, frame = cap.read(dst) if dst is not None else cap.read()
+            if not ret:
+                break
+            if keep:
+                if buf is None or buf.shape[1:] != frame.shape or n >= len(buf):
+                    grown = np.empty((max(max_frames + 1, n + 1),) + frame.shape, np.uint8)      # pages are touched on use
+                    if buf is not None and buf.shape[1:] == frame.shape:
+                        grown[:n] = buf[:n]
+                    _scratch.buf = buf = grown
+                if frame is not dst and not (dst is not None and np.shares_memory(frame, dst)):
+                    buf[n] = frame                                 # first frame of a size, or cv2 returned its own array
+                n += 1
+            count += 1
+    finally:
+        cap.release()
+    return buf[:n] if buf is not None else np.empty((0,), np.uint8)
 
 
 def temporal_median_frames(frames: List[np.ndarray], device=0) -> np.ndarray:
@@ -174,26 +215,31 @@ def bg_extract_multiple(paths: List[pathlib.Path], output_dir: pathlib.Path, fro
         device = _shard.device_for(process_id, torch.cuda.device_count())
     dev = torch.device(f"cuda:{device}" if isinstance(device, int) else device)
     torch.cuda.set_device(dev)
-    failures = []
 
-    def write(tag, bg):
-        cv2.imwrite(str(tag), bg)
-
-    stager = FrameStager(write, dev, slab_mb)
-
-    def decode(p):
-        try:
-            return p, read_frames(p, from_video, interval, max_frames), None
-        except Exception as e:  # keep going, report at the end
-            return p, [], e
-
+    os.environ.setdefault("OPENCV_FFMPEG_THREADS", "1")     # many videos in flight: one FFmpeg thread per capture, no oversubscription
     with ThreadPoolExecutor(max_workers=max(1, decode_threads)) as pool:
-        for p, frames, err in pool.map(decode, paths):
-            if err is not None or not frames:
-                failures.append((str(p), repr(err) if err else "no frames decoded"))
-                continue
-            stager.add_video(frames, (output_dir / p.name).with_suffix('.jpg'))
-    stager.flush()
+        writes = []
+
+        def write(tag, bg):                                  # JPEG encoding off the staging path
+            writes.append(pool.submit(cv2.imwrite, str(tag), bg))
+
+        stager = FrameStager(write, dev, slab_mb)
+
+        def decode(p):
+            # decode into this thread's scratch frames, then pack them into the pinned slab from this thread
+            try:
+                frames = read_frames_packed(p, from_video, interval, max_frames)
+                if not len(frames):
+                    return str(p), "no frames decoded"
+                stager.add_video(frames, (output_dir / p.name).with_suffix('.jpg'))
+                return None
+            except Exception as e:  # keep going, report at the end
+                return str(p), repr(e)
+
+        failures = [f for f in pool.map(decode, paths) if f is not None]
+        stager.flush()
+        for w in writes:
+            w.result()
     return failures
 
 
@@ -229,6 +275,8 @@ def main(argv=None):
         raise ValueError
 
     splits = _shard.contiguous_splits(video_paths, args.num_workers)
+    if args.decode_threads <= 0:
+        args.decode_threads = max(1, min(32, len(os.sched_getaffinity(0)) // max(1, sum(1 for s_ in splits if len(s_)))))
     t0 = time.perf_counter()
     _shard.run_shards(_shard_entry, splits, str(output_dir), args.from_video, args.interval, args.max_frames,
                       args.method, avg_method, args.decode_threads, args.slab_mb)

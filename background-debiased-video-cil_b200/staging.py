@@ -6,9 +6,14 @@ slab that holds several whole videos back to back (``[sum T, N]`` uint8 plus the
 when a slab is full it is copied to the device on its own stream, reduced with one
 ``temporal_median_varlen`` launch, and the ``[V, N]`` backgrounds are copied back -- while the
 decoder is already filling the other slab.
+
+``add_video`` may be called from many decoder threads at once: a thread reserves its rows under a lock and
+copies its frames into the slab outside it (numpy releases the GIL for the copy), so packing scales with the
+decoder threads instead of serialising on the caller.
 """
 from __future__ import annotations
 
+import threading
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -19,10 +24,11 @@ from . import ops as _ops  # noqa: F401  (registers torch.ops.bgdebias.*)
 
 class _Slab:
     def __init__(self, nbytes: int, device: torch.device):
-        self.host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        self.stream = torch.cuda.Stream(device)
-        self.done = torch.cuda.Event()
+        with torch.cuda.device(device):
+            self.host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.stream = torch.cuda.Stream(device)
+            self.done = torch.cuda.Event()
         self.reset()
 
     def reset(self):
@@ -33,6 +39,7 @@ class _Slab:
         self.shapes: list = []
         self.out_host: Optional[torch.Tensor] = None
         self.pending = False
+        self.filling = 0                   # reservations whose frames are still being copied in
 
 
 class FrameStager:
@@ -48,42 +55,67 @@ class FrameStager:
         self.slab_bytes = int(slab_mb) << 20
         self.slabs: List[Optional[_Slab]] = [None, None]
         self.cur = 0
-
-    def _slab(self, i: int, need: int) -> _Slab:
-        s = self.slabs[i]
-        if s is None or s.host.numel() < need:
-            if s is not None and s.pending:
-                self._drain(i)
-            self.slabs[i] = s = _Slab(max(self.slab_bytes, need), self.device)
-        return s
+        self._cv = threading.Condition()
 
     def add_video(self, frames: Sequence[np.ndarray], tag) -> None:
+        """Thread-safe.  ``frames``: a list of equal-shaped uint8 frames or one ``[T, ...]`` uint8 array."""
         T = len(frames)
         if T == 0:
             # reference: np.median([]) -> nan -> cv2.imwrite raises (extract_background.py:73-74)
             raise ValueError(f"{tag}: no frames decoded")
         shape = tuple(frames[0].shape)
+        stacked = isinstance(frames, np.ndarray)
+        if stacked:
+            if frames.dtype != np.uint8:
+                raise ValueError(f"{tag}: frames must be uint8")
+        else:
+            for t, f in enumerate(frames):
+                if tuple(f.shape) != shape or f.dtype != np.uint8:
+                    raise ValueError(f"{tag}: frame {t} differs in shape or dtype")
         N = int(np.prod(shape))
         need = T * N
-        slab = self._slab(self.cur, need)
-        if slab.pending:
-            self._drain(self.cur)
-        if slab.used and (slab.N != N or slab.used + need > slab.host.numel()):
-            self._submit(self.cur)
-            self.cur ^= 1
-            slab = self._slab(self.cur, need)
+        with self._cv:
+            slab = self._room_for(need, N)
+            off = slab.used
+            slab.N = N
+            slab.used += need
+            slab.offsets.append(slab.offsets[-1] + T)
+            slab.tags.append(tag)
+            slab.shapes.append(shape)
+            slab.filling += 1
+        try:
+            view = slab.host[off:off + need].view(T, N).numpy()
+            if stacked:
+                view[:] = frames.reshape(T, N)
+            else:
+                for t, f in enumerate(frames):
+                    view[t] = f.reshape(-1)
+        finally:
+            with self._cv:
+                slab.filling -= 1
+                self._cv.notify_all()
+
+    def _room_for(self, need: int, N: int) -> _Slab:
+        """The slab the next ``need`` bytes go to (lock held): submits the current one when it is full or holds
+        frames of another size -- after every thread still copying into it has finished -- and moves to the other."""
+        while True:
+            i = self.cur
+            slab = self.slabs[i]
+            if slab is None:
+                self.slabs[i] = slab = _Slab(max(self.slab_bytes, need), self.device)
+                return slab
             if slab.pending:
-                self._drain(self.cur)
-        slab.N = N
-        view = slab.host[slab.used:slab.used + need].view(T, N).numpy()
-        for t, f in enumerate(frames):
-            if tuple(f.shape) != shape or f.dtype != np.uint8:
-                raise ValueError(f"{tag}: frame {t} differs in shape or dtype")
-            view[t] = f.reshape(-1)
-        slab.used += need
-        slab.offsets.append(slab.offsets[-1] + T)
-        slab.tags.append(tag)
-        slab.shapes.append(shape)
+                self._drain(i)
+            if slab.used == 0 and slab.host.numel() < need:           # a video larger than the slab: grow it
+                self.slabs[i] = slab = _Slab(need, self.device)
+                return slab
+            if slab.used + need <= slab.host.numel() and (slab.used == 0 or slab.N == N):
+                return slab
+            while slab.filling:
+                self._cv.wait()
+            if self.cur == i and self.slabs[i] is slab and slab.used and not slab.pending:    # nobody else did it meanwhile
+                self._submit(i)
+                self.cur ^= 1
 
     def _submit(self, i: int) -> None:
         slab = self.slabs[i]
@@ -91,7 +123,8 @@ class FrameStager:
             return
         V, N = len(slab.tags), slab.N
         rows = slab.offsets[-1]
-        with torch.cuda.stream(slab.stream):
+        # decoder threads land here too: the current device is per thread
+        with torch.cuda.device(self.device), torch.cuda.stream(slab.stream):
             slab.dev[:slab.used].copy_(slab.host[:slab.used], non_blocking=True)
             out = torch.ops.bgdebias.temporal_median_varlen(slab.dev[:slab.used].view(rows, N),
                                                             torch.tensor(slab.offsets, dtype=torch.int64))
@@ -111,6 +144,10 @@ class FrameStager:
         slab.reset()
 
     def flush(self) -> None:
-        self._submit(self.cur)
-        for i in (self.cur ^ 1, self.cur):
-            self._drain(i)
+        """Call after every ``add_video`` has returned."""
+        with self._cv:
+            while any(sl is not None and sl.filling for sl in self.slabs):
+                self._cv.wait()
+            self._submit(self.cur)
+            for i in (self.cur ^ 1, self.cur):
+                self._drain(i)

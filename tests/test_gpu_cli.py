@@ -92,3 +92,26 @@ def test_per_video_functions_keep_the_reference_signatures(tmp_path):
     assert (tmp_path / "f.jpg").exists()
     with pytest.raises(NotImplementedError):
         cl.bg_extraction_tmf(folder, tmp_path / "g.jpg", from_video=True)
+
+
+def test_many_threads_small_slabs_mixed_sizes(tmp_path):
+    """Decoder threads reserve rows and pack concurrently while slabs rotate (1 MB slabs hold a few videos), frame
+    sizes alternate (a slab holds one size) and one video is larger than a slab."""
+    from bgdebias_b200 import extract_background as eb
+    rng = np.random.default_rng(11)
+    vdir, odir = tmp_path / "videos", tmp_path / "bg"
+    vdir.mkdir()
+    videos = {}
+    for k in range(40):
+        h, w = (H, W) if k % 3 else (32, 48)
+        T = 150 if k == 7 else int(rng.integers(1, 40))
+        fr = rng.integers(0, 256, (T, h, w, 3), dtype=np.uint8)
+        wr = cv2.VideoWriter(str(vdir / f"v{k:02d}.avi"), cv2.VideoWriter_fourcc(*"FFV1"), 25, (w, h))
+        for f in fr:
+            wr.write(f)
+        wr.release()
+        videos[f"v{k:02d}"] = fr
+    eb.main(["--video_dir", str(vdir), "--output_dir", str(odir), "--from_video", "--num_workers", "1",
+             "--decode_threads", "8", "--slab_mb", "1"])
+    for name, fr in videos.items():
+        assert (odir / f"{name}.jpg").read_bytes() == _expected_jpeg(list(fr), 1, 500, tmp_path), name

@@ -47,6 +47,32 @@ def test_read_frames_selection_matches_oracle(tmp_path, n, interval, max_frames)
         np.testing.assert_array_equal(g, fr[i])
 
 
+@pytest.mark.parametrize("n,interval,max_frames", [(20, 1, 4), (40, 2, 5), (50, 3, 500), (9, 1, 500), (9, 4, 0)])
+def test_read_frames_packed_equals_read_frames(tmp_path, n, interval, max_frames):
+    """The batched path's decoder (frames straight into a reusable per-thread scratch) keeps the same frames,
+    also when the scratch is reused for a video of another size and by several threads at once."""
+    from concurrent.futures import ThreadPoolExecutor
+    from bgdebias_b200 import extract_background as eb
+    rng = np.random.default_rng(n)
+    vids = []
+    for k, (h, w) in enumerate([(16, 24), (16, 24), (12, 8), (16, 24)]):
+        fr = rng.integers(0, 256, (n + k, h, w, 3), dtype=np.uint8)
+        _write_ffv1(tmp_path / f"v{k}.avi", fr)
+        vids.append((tmp_path / f"v{k}.avi", fr))
+
+    def check(item):
+        path, fr = item
+        got = eb.read_frames_packed(path, True, interval, max_frames).copy()
+        idx = mo.select_frame_indices(len(fr), interval, max_frames)
+        assert got.shape == (len(idx),) + fr.shape[1:]
+        np.testing.assert_array_equal(got, fr[idx])
+        return True
+
+    assert all(check(v) for v in vids)                         # one thread, scratch reused across sizes
+    with ThreadPoolExecutor(3) as ex:
+        assert all(ex.map(check, vids * 3))
+
+
 def test_read_frames_image_folder(tmp_path):
     import cv2
     from bgdebias_b200 import extract_background as eb

@@ -1,6 +1,8 @@
 """End-to-end timing of the extraction CLI on a folder of synthetic lossless videos (decode included), next to the
 reference's per-video procedure (decode + np.median, one process per core, extract_background.py:42-75,154-162)
-restated with the oracle.  usage: python tools/perf_cli.py [n_videos=48] [frames=150]"""
+restated with the oracle.  usage: [FOURCC=HFYU|mp4v|XVID] [CONTENT=noise|smooth] python tools/perf_cli.py [n_videos=48] [frames=150]
+FOURCC=HFYU CONTENT=noise (default) is the worst case for the decoder (incompressible frames, lossless codec);
+FOURCC=mp4v CONTENT=smooth is what UCF101 / HMDB51 look like (MPEG-4 part 2 in .avi, natural-image statistics)."""
 import json, os, pathlib, sys, tempfile, time
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import cv2, numpy as np
@@ -32,6 +34,8 @@ def main():
         vdir, odir = pathlib.Path(tmp) / "videos", pathlib.Path(tmp) / "bg"
         vdir.mkdir()
         base = rng.integers(0, 256, (4, H, W, 3), dtype=np.uint8)
+        if os.environ.get("CONTENT", "noise") == "smooth":
+            base = np.stack([cv2.GaussianBlur(b, (31, 31), 0) for b in base])
         t0 = time.perf_counter()
         for v in range(n_videos):
             wr = cv2.VideoWriter(str(vdir / f"v{v:04d}.avi"), cv2.VideoWriter_fourcc(*os.environ.get("FOURCC", "HFYU")), 25, (W, H))
@@ -53,7 +57,8 @@ def main():
                       "ours_cli_s": round(t_gpu, 3), "ours_frames_per_s": round(n / t_gpu, 1),
                       "reference_procedure_s": round(t_cpu, 3), "reference_frames_per_s": round(n / t_cpu, 1),
                       "speedup": round(t_cpu / t_gpu, 2), "identical_jpegs": same,
-                      "note": "decode (OpenCV/FFmpeg, FFV1) is on the host in both arms; ours decodes with a thread pool into a pinned slab and reduces many videos per launch"}))
+                      "codec": os.environ.get("FOURCC", "HFYU"), "content": os.environ.get("CONTENT", "noise"),
+                      "note": "decode (OpenCV/FFmpeg) is on the host in both arms; ours decodes with a thread pool into a pinned slab and reduces many videos per launch"}))
 
 
 if __name__ == "__main__":
