@@ -1,6 +1,6 @@
 """End-to-end timing of the extraction CLI on a folder of synthetic lossless videos (decode included), next to the
 reference's per-video procedure (decode + np.median, one process per core, extract_background.py:42-75,154-162)
-restated with the oracle.  usage: [FOURCC=HFYU|mp4v|XVID] [CONTENT=noise|smooth] python tools/perf_cli.py [n_videos=48] [frames=150]
+restated with the oracle.  usage: [FOURCC=HFYU|mp4v|XVID] [CONTENT=noise|smooth] [WORKERS=gpus] python tools/perf_cli.py [n_videos=48] [frames=150]
 FOURCC=HFYU CONTENT=noise (default) is the worst case for the decoder (incompressible frames, lossless codec);
 FOURCC=mp4v CONTENT=smooth is what UCF101 / HMDB51 look like (MPEG-4 part 2 in .avi, natural-image statistics)."""
 import json, os, pathlib, sys, tempfile, time
@@ -44,7 +44,9 @@ def main():
                 wr.write(f)
             wr.release()
         print(f"wrote {n_videos} x {T} frames in {time.perf_counter() - t0:.1f} s", file=sys.stderr)
-        argv = ["--video_dir", str(vdir), "--output_dir", str(odir), "--from_video", "--num_workers", "1", "--decode_threads", str(cores)]
+        workers = int(os.environ.get("WORKERS", "1"))               # GPU shards (one process per GPU)
+        argv = ["--video_dir", str(vdir), "--output_dir", str(odir), "--from_video", "--num_workers", str(workers),
+                "--decode_threads", str(max(1, cores // workers))]
         eb.main(argv)                                           # warm-up run (CUDA context, pinned slabs) ...
         for f in odir.glob("*.jpg"): f.unlink()
         t0 = time.perf_counter(); eb.main(argv); t_gpu = time.perf_counter() - t0
@@ -53,7 +55,7 @@ def main():
             list(ex.map(_cpu_one, paths[:cores]))               # warm-up
             t0 = time.perf_counter(); n = sum(ex.map(_cpu_one, paths)); t_cpu = time.perf_counter() - t0
         same = all((odir / (pathlib.Path(p).stem + ".jpg")).read_bytes() == pathlib.Path(p + ".cpu.jpg").read_bytes() for p in paths)
-    print(json.dumps({"videos": n_videos, "frames": n, "host_cores": cores,
+    print(json.dumps({"videos": n_videos, "frames": n, "host_cores": cores, "gpu_shards": workers,
                       "ours_cli_s": round(t_gpu, 3), "ours_frames_per_s": round(n / t_gpu, 1),
                       "reference_procedure_s": round(t_cpu, 3), "reference_frames_per_s": round(n / t_cpu, 1),
                       "speedup": round(t_cpu / t_gpu, 2), "identical_jpegs": same,
