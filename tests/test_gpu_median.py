@@ -73,8 +73,8 @@ def test_random_all_T(bgd, T, variant):
 
 
 @pytest.mark.parametrize("pattern", ["constant", "two_valued", "saturated", "sorted", "reverse_sorted",
-                                     "near_ties", "narrow_high", "all255", "all0"])
-@pytest.mark.parametrize("T", [6, 37, 96, 180])
+                                     "near_ties", "narrow_high", "all255", "all0", "static_scene"])
+@pytest.mark.parametrize("T", [6, 37, 96, 180, 300])
 def test_patterns(bgd, pattern, T):
     ops, cabi = bgd
     rng = np.random.default_rng(hash((pattern, T)) % (2 ** 32))
@@ -91,6 +91,14 @@ def test_patterns(bgd, pattern, T):
         fr = np.sort(rng.integers(0, 256, (T, N), dtype=np.uint8), axis=0)[::-1].copy()
     elif pattern == "near_ties":
         fr = (rng.integers(2, 254, (1, N)) + rng.integers(-2, 3, (T, N))).astype(np.uint8)
+    elif pattern == "static_scene":
+        # a fixed background, a few noisy columns and a block passing through: most warps never part the two middles of an
+        # even T, some part them late in a few lanes only
+        fr = np.repeat(rng.integers(0, 256, (1, N), dtype=np.uint8), T, axis=0)
+        noisy = rng.random(N) < 0.02
+        fr[:, noisy] = (fr[:, noisy].astype(np.int16) + rng.integers(-1, 2, (T, int(noisy.sum())))).clip(0, 255).astype(np.uint8)
+        for t in range(T):
+            fr[t, (37 * t) % (N - 64):(37 * t) % (N - 64) + 64] = 200 + t % 7
     elif pattern == "narrow_high":
         fr = rng.integers(250, 256, (T, N), dtype=np.uint8)
     elif pattern == "all255":
