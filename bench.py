@@ -346,14 +346,22 @@ def run_ours(args):
         mean, std = torch.tensor([123.675, 116.28, 103.53]), torch.tensor([58.395, 57.12, 57.375])
         lut = ops.make_fg_lut(mean.tolist(), std.tolist(), dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > L2 (126 MB)
-        mix = lambda: torch.ops.bgdebias.bgmix_blend(fg, pool, idx, top, left, app, lut, mean, std, 0.5, "NTCHW")
+        # the timed call goes straight to the C ABI on torch's current stream (what the custom op does after its checks):
+        # the bracket then holds the launch, not ~10 us of Python dispatch with the GPU idle
+        o = torch.empty((B, Tm, 3, Hm, Wm), dtype=torch.float32, device=dev)
+        c_mean, c_std = _cabi.f32x3(mean.tolist()), _cabi.f32x3(std.tolist())
+        cur = torch.cuda.current_stream(dev).cuda_stream
+        mix = lambda: _cabi.check(L.bgd_bgmix_blend_f32(fg.data_ptr(), B, Tm, Hm, Wm, pool.data_ptr(), P, 256, 341, idx.data_ptr(),
+                                                        top.data_ptr(), left.data_ptr(), app.data_ptr(), lut.data_ptr(), c_mean, c_std,
+                                                        0.5, 0, o.data_ptr(), cur))
         for _ in range(3):
             mix()
+        assert torch.equal(o, torch.ops.bgdebias.bgmix_blend(fg, pool, idx, top, left, app, lut, mean, std, 0.5, "NTCHW"))
         times = []
         for _ in range(max(5, args.steps)):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); o = mix(); b.record(); torch.cuda.synchronize()
+            a.record(); mix(); b.record(); torch.cuda.synchronize()
             times.append(a.elapsed_time(b))
         mix_ms = sorted(times)[len(times) // 2]
         mix_bytes = B * (Tm * Hm * Wm * 3 * 5 + Hm * Wm * 3 * 4)
@@ -414,14 +422,18 @@ def run_ours(args):
             crops = [torch.randint(0, 256, (Tm, *sizes[i % len(sizes)], 3), dtype=torch.uint8, generator=gc) for i in range(B)]
             buf, geom = ops.pack_clips(crops)
             d_buf = buf.to(dev)
-            tail = lambda: torch.ops.bgdebias.bgmix_resize_blend(d_buf, geom, Tm, Hm, Wm, pool, idx, top, left, app, lut, mean, std, 0.5, "NTCHW")
+            o2 = torch.empty((B, Tm, 3, Hm, Wm), dtype=torch.float32, device=dev)
+            gptr = ctypes.cast(geom.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+            tail = lambda: _cabi.check(L.bgd_bgmix_resize_blend_f32(
+                d_buf.data_ptr(), d_buf.numel(), gptr, B, Tm, Hm, Wm, pool.data_ptr(), 0, P, 256, 341, idx.data_ptr(), top.data_ptr(),
+                left.data_ptr(), app.data_ptr(), lut.data_ptr(), c_mean, c_std, 0.5, 0, o2.data_ptr(), cur))
             for _ in range(3):
                 tail()
             times = []
             for _ in range(max(5, args.steps)):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); o2 = tail(); b.record(); torch.cuda.synchronize()
+                a.record(); tail(); b.record(); torch.cuda.synchronize()
                 times.append(a.elapsed_time(b))
             tail_ms = sorted(times)[len(times) // 2]
             tail_bytes = sum(c.numel() for c in crops) + B * Hm * Wm * 3 * 4 * (1 + Tm)
