@@ -199,3 +199,27 @@ def test_background_store_slots_without_gpu():
         store.view(["n5"])
     with pytest.raises(ValueError):
         store.ensure(["bad"], lambda n: torch.zeros(3, 9, 9, dtype=torch.uint8))
+
+
+def _fake_person_detector():
+    """Detector plug-in for the type B/C shim: 'person' iff the image's top-left pixel is white."""
+    return lambda img: [0, 17] if img[0, 0, 0] > 200 else [17]
+
+
+def test_type_b_and_c_shim_selection_rule(tmp_path, monkeypatch):
+    """type_b_and_c_bg.py:42-54: copy the backgrounds in which class 0 is not predicted; out_dir must be new."""
+    import cv2
+    from bgdebias_b200 import type_b_and_c_bg as tb
+    src = tmp_path / "bg"; src.mkdir()
+    for i in range(5):
+        img = np.full((8, 8, 3), 255 if i % 2 else 10, np.uint8)
+        cv2.imwrite(str(src / f"v{i}.png"), img)
+    monkeypatch.chdir(tmp_path)
+    out = tmp_path / "type_c"
+    rec = tb.main(["-i", str(src), "-o", str(out), "--glob_pattern", "*.png", "--detector", "test_host_logic:_fake_person_detector"])
+    assert sorted(p.name for p in out.iterdir()) == ["v0.png", "v2.png", "v4.png"]
+    assert [r["copied"] for r in rec] == [True, False, True, False, True] and (tmp_path / "detection.json").exists()
+    with pytest.raises(FileExistsError):
+        tb.main(["-i", str(src), "-o", str(out), "--detector", "test_host_logic:_fake_person_detector"])
+    with pytest.raises(RuntimeError, match="detector"):
+        tb.main(["-i", str(src), "-o", str(tmp_path / "x")])           # detectron2 is absent here: loud failure
