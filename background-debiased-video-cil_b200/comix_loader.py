@@ -26,9 +26,11 @@ mixed sizes are packed by ``host_collate`` and resized (cv2 INTER_LINEAR, bit fo
 """
 from __future__ import annotations
 
+import os
 import os.path as osp
 import pathlib
 import random
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -420,7 +422,10 @@ def bg_extraction_tmf(data_path, dest, from_video=False, device='cuda'):
     if from_video:
         raise NotImplementedError
     data_path = pathlib.Path(data_path)
-    frames = [cv2.imread(str(f)) for f in data_path.glob('*')]
+    files = [str(f) for f in data_path.glob('*')]
+    # JPEG decode dominates this call: spread it over the host cores (cv2 releases the GIL; the median ignores order)
+    with ThreadPoolExecutor(max_workers=min(16, len(os.sched_getaffinity(0)))) as ex:
+        frames = list(ex.map(cv2.imread, files))
     frames = [f for f in frames if f is not None]
     if not frames:
         raise ValueError(f"no readable frames under {data_path}")     # reference: nan median -> imwrite raises
