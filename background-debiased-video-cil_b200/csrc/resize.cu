@@ -34,7 +34,10 @@
 namespace bgd {
 namespace {
 
-constexpr int kTileW = 32, kTileH = 8, kThreads = kTileW * kTileH;
+#ifndef BGD_RESIZE_TILEH
+#define BGD_RESIZE_TILEH 8
+#endif
+constexpr int kTileW = 32, kTileH = BGD_RESIZE_TILEH, kThreads = kTileW * kTileH;
 #ifndef BGD_RESIZE_UNROLL
 #define BGD_RESIZE_UNROLL 1
 #endif
