@@ -49,6 +49,9 @@ SIGNATURES = {
                                               _vp, _vp, _vp, _vp, _f32p, _f32p, _c.c_double, _c.c_int, _vp, _vp]),
     "bgd_bgmix_blend_f32_host": (_c.c_int, _blend_common + [_c.POINTER(_c.c_double), _c.c_int]),
     "bgd_resize_bilinear_u8": (_c.c_int, [_vp, _c.c_int64, _i64p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64, _vp, _vp]),
+    "bgd_bgmix_resize_blend_f32_host": (_c.c_int, [_vp, _c.c_int64, _i64p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64,
+                                                   _vp, _c.c_int64, _c.c_int64, _c.c_int64, _vp, _vp, _vp, _vp, _vp,
+                                                   _f32p, _f32p, _c.c_double, _c.c_int, _vp, _c.POINTER(_c.c_double), _c.c_int]),
     "bgd_bgmix_resize_blend_f32": (_c.c_int, [_vp, _c.c_int64, _i64p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64,
                                               _vp, _c.c_int, _c.c_int64, _c.c_int64, _c.c_int64,
                                               _vp, _vp, _vp, _vp, _vp, _f32p, _f32p, _c.c_double, _c.c_int, _vp, _vp]),

@@ -439,6 +439,17 @@ def run_ours(args):
             tail_bytes = sum(c.numel() for c in crops) + B * Hm * Wm * 3 * 4 * (1 + Tm)
             two = torch.ops.bgdebias.bgmix_blend(torch.ops.bgdebias.resize_bilinear(d_buf, geom, Tm, Hm, Wm), pool, idx, top, left,
                                                  app, lut, mean, std, 0.5, "NTCHW")
+            # end to end: pinned packed crops + draws in host memory -> training tensor on device + checksum back
+            h_buf = torch.empty(buf.shape, dtype=torch.uint8, pin_memory=True); h_buf.copy_(buf)
+            call2 = lambda: _cabi.check(L.bgd_bgmix_resize_blend_f32_host(
+                h_buf.data_ptr(), h_buf.numel(), gptr, B, Tm, Hm, Wm, pool.data_ptr(), P, 256, 341, hi.ctypes.data, ht.ctypes.data,
+                hl.ctypes.data, ha.ctypes.data, lut.data_ptr(), c_mean, c_std, 0.5, 0, d_out.data_ptr(), ctypes.byref(chk), local_rank))
+            call2(); call2()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                call2()
+            tail_e2e = 5 * B / (time.perf_counter() - t0)
+            tail_e2e_ok = bool(torch.equal(d_out, o2))
             tail_cpu = None
             if rank == 0 and world == 1:
                 import cv2
@@ -459,7 +470,9 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "note": "integer-ALU bound (issue slots ~70 % busy, profiles/r1_ncu_resize_blend.txt), not HBM bound"},
-                "cpu_baseline": tail_cpu, "parity_spotcheck": bool(torch.equal(o2, two))}
+                "e2e": {"value": world * tail_e2e, "unit": "clips/s", "h2d_bytes_per_step": int(h_buf.numel() + B * 13),
+                        "d2h_bytes_per_step": 8},
+                "cpu_baseline": tail_cpu, "parity_spotcheck": bool(torch.equal(o2, two)) and tail_e2e_ok}
             del d_buf, o2, two
         except Exception as e:
             bgmix["with_resize"] = {"error": repr(e)}

@@ -216,6 +216,18 @@ int bgd_bgmix_resize_blend_f32(const uint8_t *d_src, int64_t src_bytes, const in
                                const float *d_fg_lut, const float *h_bg_mean, const float *h_bg_std,
                                double alpha, int layout, float *d_out, void *stream);
 
+/* Host-buffer form of bgd_bgmix_resize_blend_f32, as bgd_bgmix_blend_f32_host is for the blend: the packed crops
+ * (h_src, pinned or pageable) and the per-sample draws live in host memory -- what a DataLoader collate hands over when
+ * the pipeline stops after MultiScaleCrop (config :129-135) -- the fp32 pool and the table are device resident.  Copies in,
+ * runs the fused launch, leaves the training tensor in d_out and returns when the stream is idle; h_checksum (may be NULL)
+ * receives the sum of the output elements. */
+int bgd_bgmix_resize_blend_f32_host(const uint8_t *h_src, int64_t src_bytes, const int64_t *h_geom, int64_t B,
+                                    int64_t T, int64_t H, int64_t W, const float *d_bg_pool, int64_t P,
+                                    int64_t Hb, int64_t Wb, const int32_t *h_bg_idx, const int32_t *h_top,
+                                    const int32_t *h_left, const uint8_t *h_apply, const float *d_fg_lut,
+                                    const float *h_bg_mean, const float *h_bg_std, double alpha, int layout,
+                                    float *d_out, double *h_checksum, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,40 @@ def test_full_size_batch_properties(env):
     assert torch.equal(fused, exp)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_entry_point(env, pinned):
+    """bgd_bgmix_resize_blend_f32_host: packed crops and draws in host memory (pageable or pinned) -> training tensor on the
+    device, equal to the device-resident op, plus the checksum; draws outside the pool are refused."""
+    import ctypes
+    ops, cabi = env[0], env[1]
+    rng = np.random.default_rng(12)
+    T, H, W, P = 3, 40, 40, 4
+    clips = [rng.integers(0, 256, (T, h, w, 3), dtype=np.uint8) for h, w in [(48, 48), (40, 40), (30, 36), (44, 33), (36, 30)]]
+    B = len(clips)
+    buf, geom = ops.pack_clips(clips, pin=pinned)
+    dev = torch.device("cuda")
+    pool = torch.from_numpy(rng.integers(0, 256, (P, 3, 48, 64)).astype(np.float32)).to(dev)
+    idx = rng.integers(0, P, B).astype(np.int32); top = rng.integers(0, 9, B).astype(np.int32)
+    left = rng.integers(0, 25, B).astype(np.int32); app = np.array([1, 0, 1, 1, 0], np.uint8)
+    lut = ops.make_fg_lut(bo.DEFAULT_MEAN, bo.DEFAULT_STD, dev)
+    out = torch.empty((B, T, 3, H, W), dtype=torch.float32, device=dev)
+    chk = ctypes.c_double()
+    gptr = ctypes.cast(geom.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+    call = lambda idx_: cabi.lib().bgd_bgmix_resize_blend_f32_host(                     # noqa: E731
+        buf.data_ptr(), buf.numel(), gptr, B, T, H, W, pool.data_ptr(), P, 48, 64, idx_.ctypes.data, top.ctypes.data,
+        left.ctypes.data, app.ctypes.data, lut.data_ptr(), cabi.f32x3(bo.DEFAULT_MEAN), cabi.f32x3(bo.DEFAULT_STD), 0.5, 0,
+        out.data_ptr(), ctypes.byref(chk), 0)
+    cabi.check(call(idx))
+    t = lambda a: torch.from_numpy(a).to(dev)                                           # noqa: E731
+    exp = torch.ops.bgdebias.bgmix_resize_blend(buf.to(dev), geom, T, H, W, pool, t(idx), t(top), t(left), t(app), lut,
+                                                torch.tensor(bo.DEFAULT_MEAN), torch.tensor(bo.DEFAULT_STD), 0.5, "NTCHW")
+    assert torch.equal(out, exp)
+    assert abs(chk.value - float(exp.double().sum())) <= 1e-6 * max(1.0, abs(chk.value))
+    bad = idx.copy(); bad[0] = P
+    with pytest.raises(ValueError):
+        cabi.check(call(bad))
+
+
 def test_errors(env):
     ops = env[0]
     clip = torch.zeros((1, 4, 4, 3), dtype=torch.uint8)
