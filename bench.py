@@ -463,12 +463,17 @@ def run_ours(args):
                 tc = time.perf_counter() - tc
                 tail_cpu = {"value": 4 * len(frames) / Tm / tc, "unit": "clips/s", "cores": 1, "kind": "reference",
                             "sample": f"{4 * len(frames)} cv2.resize(frame, (224, 224), INTER_LINEAR) calls (the Resize step alone, 8 per clip), one thread"}
+            tail_traffic = None
+            try:
+                tail_traffic = json.loads((ROOT / "profiles" / "r1_traffic_resize_blend.json").read_text())["dram_bytes_per_algorithmic_byte"] * tail_bytes
+            except Exception:
+                pass
             bgmix["with_resize"] = {
                 "metric": "bgmix_clips_per_sec", "value": world * B / (tail_ms * 1e-3), "unit": "clips/s", "ms_per_step": tail_ms,
                 "config": {"workload": "configs[4] with the foreground as MultiScaleCrop-sized uint8 crops (168..256 px, packed), "
                                        "Resize((224,224)) + Normalize + FormatShape + blend in one launch"},
                 "roofline": {"bound": "hbm", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peak, "traffic": tail_traffic,
                              "note": "integer-ALU bound (issue slots ~70 % busy, profiles/r1_ncu_resize_blend.txt), not HBM bound"},
                 "e2e": {"value": world * tail_e2e, "unit": "clips/s", "h2d_bytes_per_step": int(h_buf.numel() + B * 13),
                         "d2h_bytes_per_step": 8},
