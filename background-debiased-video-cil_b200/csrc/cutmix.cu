@@ -27,6 +27,11 @@ __device__ __forceinline__ uint32_t mix4(uint32_t a, uint32_t m, uint32_t s)
     return r;
 }
 
+#ifndef BGD_CUTMIX_UNROLL
+#define BGD_CUTMIX_UNROLL 2
+#endif
+constexpr int kCutmixUnroll = BGD_CUTMIX_UNROLL;
+
 // n16 16-byte vectors, then a scalar tail; mask_sum accumulates the mask bytes of channel 0 (element index % 3 == 0)
 __global__ void __launch_bounds__(256) cutmix_kernel(const uint8_t *__restrict__ actor, const uint8_t *__restrict__ mask,
                                                      const uint8_t *__restrict__ scene, uint8_t *__restrict__ out, int64_t n,
@@ -34,24 +39,43 @@ __global__ void __launch_bounds__(256) cutmix_kernel(const uint8_t *__restrict__
 {
     const int64_t n16 = n / 16;
     unsigned long long local = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(actor) + i);
-        const uint4 m = __ldcs(reinterpret_cast<const uint4 *>(mask) + i);
-        const uint4 s = __ldcs(reinterpret_cast<const uint4 *>(scene) + i);
-        __stcs(reinterpret_cast<uint4 *>(out) + i, make_uint4(mix4(a.x, m.x, s.x), mix4(a.y, m.y, s.y), mix4(a.z, m.z, s.z), mix4(a.w, m.w, s.w)));
-        if (mask_sum) {
-            // channel-0 bytes of this vector: element index = 16 i + b with (16 i + b) % 3 == 0, i.e. b % 3 == (3 - i % 3) % 3;
-            // one byte-selector word per 4 bytes and phase, summed with dp4a
-            const int ph = (int)(i % 3);
-            const uint32_t s0 = ph == 0 ? 0x01000001u : (ph == 1 ? 0x00010000u : 0x00000100u);   // bytes 0..3
-            const uint32_t s1 = ph == 0 ? 0x00010000u : (ph == 1 ? 0x00000100u : 0x01000001u);   // bytes 4..7
-            const uint32_t s2 = ph == 0 ? 0x00000100u : (ph == 1 ? 0x01000001u : 0x00010000u);   // bytes 8..11
-            uint32_t acc = __dp4a(m.x, s0, 0u);
-            acc = __dp4a(m.y, s1, acc);
-            acc = __dp4a(m.z, s2, acc);
-            acc = __dp4a(m.w, s0, acc);                  // bytes 12..15 repeat the pattern of bytes 0..3
-            local += acc;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto sum_channel0 = [&](const uint4 &m, int64_t i) {
+        // channel-0 bytes of this vector: element index = 16 i + b with (16 i + b) % 3 == 0, i.e. b % 3 == (3 - i % 3) % 3;
+        // one byte-selector word per 4 bytes and phase, summed with dp4a
+        const int ph = (int)(i % 3);
+        const uint32_t s0 = ph == 0 ? 0x01000001u : (ph == 1 ? 0x00010000u : 0x00000100u);   // bytes 0..3
+        const uint32_t s1 = ph == 0 ? 0x00010000u : (ph == 1 ? 0x00000100u : 0x01000001u);   // bytes 4..7
+        const uint32_t s2 = ph == 0 ? 0x00000100u : (ph == 1 ? 0x01000001u : 0x00010000u);   // bytes 8..11
+        uint32_t acc = __dp4a(m.x, s0, 0u);
+        acc = __dp4a(m.y, s1, acc);
+        acc = __dp4a(m.z, s2, acc);
+        acc = __dp4a(m.w, s0, acc);                      // bytes 12..15 repeat the pattern of bytes 0..3
+        local += acc;
+    };
+    auto mix16 = [](const uint4 &a, const uint4 &m, const uint4 &s) {
+        return make_uint4(mix4(a.x, m.x, s.x), mix4(a.y, m.y, s.y), mix4(a.z, m.z, s.z), mix4(a.w, m.w, s.w));
+    };
+    const uint4 *va = reinterpret_cast<const uint4 *>(actor), *vm = reinterpret_cast<const uint4 *>(mask),
+                *vs = reinterpret_cast<const uint4 *>(scene);
+    uint4 *vo = reinterpret_cast<uint4 *>(out);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kCutmixUnroll - 1) * stride < n16; i += kCutmixUnroll * stride) {     // kCutmixUnroll vectors of each stream in flight
+        uint4 a[kCutmixUnroll], m[kCutmixUnroll], s[kCutmixUnroll];
+#pragma unroll
+        for (int u = 0; u < kCutmixUnroll; ++u) {
+            a[u] = __ldcs(va + i + u * stride); m[u] = __ldcs(vm + i + u * stride); s[u] = __ldcs(vs + i + u * stride);
         }
+#pragma unroll
+        for (int u = 0; u < kCutmixUnroll; ++u) {
+            __stcs(vo + i + u * stride, mix16(a[u], m[u], s[u]));
+            if (mask_sum) sum_channel0(m[u], i + u * stride);
+        }
+    }
+    for (; i < n16; i += stride) {
+        const uint4 a = __ldcs(va + i), m = __ldcs(vm + i), s = __ldcs(vs + i);
+        __stcs(vo + i, mix16(a, m, s));
+        if (mask_sum) sum_channel0(m, i);
     }
     if (blockIdx.x == 0 && threadIdx.x < (int)(n - n16 * 16)) {          // tail (< 16 bytes)
         const int64_t j = n16 * 16 + threadIdx.x;
