@@ -26,6 +26,16 @@ _blend_common = [_vp, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64,       # fg
                  _vp, _vp, _vp, _vp, _vp,                                   # bg_idx, top, left, apply, lut
                  _f32p, _f32p, _c.c_double, _c.c_int, _vp]                  # mean, std, alpha, layout, out
 
+class RaggedSlot(_c.Structure):
+    """``bgd_ragged_slot`` of include/bgdebias.h (40 bytes)."""
+    _fields_ = [("offset", _c.c_int64), ("h", _c.c_int32), ("w", _c.c_int32), ("Hb", _c.c_int32), ("Wb", _c.c_int32),
+                ("xtab", _c.c_int32), ("ytab", _c.c_int32), ("kx", _c.c_int32), ("ky", _c.c_int32)]
+
+
+_ragged_common = [_c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64,            # B, T, H, W
+                  _vp, _vp, _c.c_int64, _vp,                                 # pool, slots, P, tables
+                  _vp, _vp, _vp, _vp]                                        # bg_idx, top, left, apply
+
 # name -> (restype, argtypes): the declarations of include/bgdebias.h, in header order
 SIGNATURES = {
     "bgd_abi_version": (_c.c_int, []),
@@ -48,6 +58,10 @@ SIGNATURES = {
                                               _vp, _c.c_int, _c.c_int64, _c.c_int64, _c.c_int64,
                                               _vp, _vp, _vp, _vp, _f32p, _f32p, _c.c_double, _c.c_int, _vp, _vp]),
     "bgd_bgmix_blend_f32_host": (_c.c_int, _blend_common + [_c.POINTER(_c.c_double), _c.c_int]),
+    "bgd_aa_resize_table": (_c.c_int, [_c.c_int64, _c.c_int64, _c.POINTER(_c.c_int32), _vp, _c.c_int64]),
+    "bgd_aa_resize_u8_f32": (_c.c_int, [_vp, _c.POINTER(RaggedSlot), _vp, _vp, _vp]),
+    "bgd_bgmix_blend_ragged_f32": (_c.c_int, [_vp] + _ragged_common + [_vp, _f32p, _f32p, _c.c_double, _c.c_int, _vp, _vp]),
+    "bgd_bgmix_blend_ragged_normfg_f32": (_c.c_int, [_vp] + _ragged_common + [_f32p, _f32p, _c.c_double, _c.c_int, _vp, _vp]),
     "bgd_resize_bilinear_u8": (_c.c_int, [_vp, _c.c_int64, _i64p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64, _vp, _vp]),
     "bgd_bgmix_resize_blend_f32_host": (_c.c_int, [_vp, _c.c_int64, _i64p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64,
                                                    _vp, _c.c_int64, _c.c_int64, _c.c_int64, _vp, _vp, _vp, _vp, _vp,

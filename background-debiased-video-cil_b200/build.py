@@ -21,7 +21,7 @@ LIB = PKG / os.environ.get("BGD_BUILD_OUT", "libbgdebias_b200.so")
 EXTRA_DEFINES = [d for d in os.environ.get("BGD_BUILD_DEFINES", "").split() if d]
 SOURCES = ["api.cu", "median_swar.cu", "median_bitsliced.cu", "median_tma_planner.cu", "median_colplane_c1.cu",
            "median_colplane_c2.cu", "median_colplane_c4.cu", "median_ldsm_q0.cu", "median_ldsm_q1.cu",
-           "median_ldsm_q2.cu", "median_ldsm_q3.cu", "median_ldsm_q4.cu", "median_ldsm_q5.cu", "bgmix.cu", "nanreduce.cu", "cutmix.cu", "resize.cu"]
+           "median_ldsm_q2.cu", "median_ldsm_q3.cu", "median_ldsm_q4.cu", "median_ldsm_q5.cu", "bgmix.cu", "raggedmix.cu", "nanreduce.cu", "cutmix.cu", "resize.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         list(ex.map(compile_one, SOURCES))
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
+    link = [nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
             *[str(OBJ / (s + ".o")) for s in SOURCES]]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode:

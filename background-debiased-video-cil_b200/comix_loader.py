@@ -37,7 +37,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .pool import BackgroundPool, BackgroundStore, resize_like_reference, resized_hw
+from .pool import AATables, BackgroundPool, BackgroundStore, RaggedPool, resize_like_reference, resized_hw
 
 try:  # mmaction is optional: register into its registries when it is importable
     from mmaction.datasets import RawframeDataset as _MMRawframeDataset
@@ -284,11 +284,17 @@ class BackgroundMixDataset(_Base):
         only draws ``bg_idx`` / crop offsets; pixels are mixed per batch by :meth:`gpu_collate`."""
         th, tw = self.bg_crop_size
         if self.device_mix:
-            if not self.back_ground_from_bg_dir:
-                raise NotImplementedError("device_mix=True needs a background directory pool "
-                                          "(back_ground_from_bg_dir=True)")
-            bg_idx = torch.randint(len(self.bg_files), (1,)).item()
-            h, w = self._pool_hw()
+            if self.back_ground_from_bg_dir:
+                bg_idx = torch.randint(len(self.bg_files), (1,)).item()
+                h, w = self._bg_hw(bg_idx)                # RandomCrop sees the DRAWN image after Resize (:72-73,139-140)
+            else:
+                # random frame of a random video (:133-136): same draws, the decoded uint8 frame travels with the sample
+                video = random.choice(self.video_infos)
+                frame_index = random.randint(self.start_index, video['total_frames'] - 1 + self.start_index)
+                img = self._read_bg(osp.join(video['frame_dir'], self.filename_tmpl.format(frame_index)))
+                h, w = self._resized_hw(int(img.shape[1]), int(img.shape[2]))
+                result['bg_img'] = img.to(torch.uint8)
+                bg_idx = -2                               # to pass sanity check
             top, left = draw_crop(h, w, (th, tw))
             result['bg_idx'], result['bg_top'], result['bg_left'], result['bg_apply'] = bg_idx, top, left, 1
             return result
@@ -315,39 +321,66 @@ class BackgroundMixDataset(_Base):
         result['bg_idx'] = bg_idx
         return result
 
-    def _pool_hw(self) -> tuple:
-        """Size of pool images after Resize, without touching the GPU (needs one image header)."""
+    def _resized_hw(self, h: int, w: int) -> tuple:
+        return (h, w) if self.bg_resize is None else resized_hw(h, w, self.bg_resize)
+
+    def _bg_hw(self, bg_idx: int) -> tuple:
+        """Size after Resize of ``bg_files[bg_idx]`` without touching the GPU: from the resident pool / store when they
+        know the file, else from the image header (cached per path; DataLoader workers take this road)."""
         if self._pool is not None and tuple(self.bg_files) == self._pool_key:
-            return self._pool.hw
-        if self._store is not None and len(self._store):
-            return self._store.hw                      # one shape per store
-        key = self.bg_files[0] if self.bg_files else None
-        if key not in self._resized_cache:
-            img = self._read_bg(key)
-            h, w = int(img.shape[1]), int(img.shape[2])
-            self._resized_cache[key] = (h, w) if self.bg_resize is None else resized_hw(h, w, self.bg_resize)
-        return self._resized_cache[key]
+            return self._pool.hw_of(bg_idx)
+        path = self.bg_files[bg_idx]
+        if self._store is not None and path in self._store.slot_of:
+            return self._store.hw_of(self._store.slot_of[path])
+        if path not in self._resized_cache:
+            if self._bg_reader is not None:
+                img = torch.as_tensor(self._bg_reader(path))
+                h, w = int(img.shape[1]), int(img.shape[2])
+            else:
+                from PIL import Image
+                with Image.open(path) as im:              # header only
+                    w, h = im.size
+            self._resized_cache[path] = self._resized_hw(h, w)
+        return self._resized_cache[path]
+
+    def _pool_hw(self) -> tuple:
+        """Size after Resize of the first pool image (kept for callers that warm the size cache before forking)."""
+        return self._bg_hw(0)
 
     # ---- batch API (device_mix=True) -------------------------------------------------------------
     def mix_batch_on_device(self, fg_u8: torch.Tensor, bg_idx, bg_top, bg_left, bg_apply,
                             img_mean: Optional[Sequence[float]] = None, img_std: Optional[Sequence[float]] = None,
                             layout: str = "NTCHW", fg_geom: Optional[torch.Tensor] = None,
-                            fg_frames: Optional[int] = None) -> torch.Tensor:
+                            fg_frames: Optional[int] = None, bg_imgs: Optional[Sequence[torch.Tensor]] = None,
+                            bg_slot=None) -> torch.Tensor:
         """uint8 ``[B,T,H,W,3]`` (host or device) + per-sample draws -> fp32 ``[B,T,3,H,W]`` on the device.
         ``img_mean``/``img_std`` are the foreground's ``Normalize`` parameters (default: the bg ones,
         as in every shipped config).
 
+        The background of sample b is pool image ``bg_idx[b]`` -- from the dense fp32 cache when the pool has one
+        image size and fits, else from the ragged uint8 store with ``Resize`` inside the launch -- or, in random-frame
+        mode (``back_ground_from_bg_dir=False``), ``bg_imgs[bg_slot[b]]``: the uint8 frames the batch drew.
+
         Clips whose size is not ``bg_crop_size`` -- a pipeline that stops before the final
-        ``Resize((224, 224), keep_ratio=False)`` (config :136) -- are resized inside the same launch with cv2's
-        INTER_LINEAR arithmetic: either a stacked batch of one other size, or packed crops of mixed sizes
+        ``Resize((224, 224), keep_ratio=False)`` (config :136) -- are resized with cv2's INTER_LINEAR arithmetic, inside
+        the blend launch for a dense pool: either a stacked batch of one other size, or packed crops of mixed sizes
         (``fg_u8`` flat, ``fg_geom`` int64 ``[B,5]``, ``fg_frames`` = T; see ``ops.pack_clips``)."""
         dev = self.device
-        pool = self.device_pool()
         mean = self.bg_mean if img_mean is None else img_mean
         std = self.bg_std if img_std is None else img_std
         lut = self._lut(tuple(mean), tuple(std))
         as_dev = lambda v, dt: torch.as_tensor(v, dtype=dt).to(dev, non_blocking=True)   # noqa: E731
         th, tw = self.bg_crop_size
+        top, left, app = as_dev(bg_top, torch.int32), as_dev(bg_left, torch.int32), as_dev(bg_apply, torch.uint8)
+        if bg_imgs is not None:
+            batch_pool = RaggedPool(self.bg_resize, dev, tables=self._aa_tables())
+            batch_pool.append(bg_imgs)
+            ragged, dense, rows = batch_pool, None, as_dev(bg_slot, torch.int32)
+        else:
+            pool = self.device_pool()
+            ragged, dense = pool.ragged, pool.tensor
+            rows = pool.rows(as_dev(bg_idx, torch.int32).clamp(min=0))
+        mean_t, std_t = torch.tensor(self.bg_mean), torch.tensor(self.bg_std)
         if fg_geom is None and tuple(fg_u8.shape[2:4]) != (th, tw):
             B, T, h, w, _ = fg_u8.shape
             frame = h * w * 3
@@ -355,16 +388,21 @@ class BackgroundMixDataset(_Base):
             flat = fg_u8.reshape(-1)
             fg_u8 = torch.cat([flat, flat.new_zeros(4 + (-flat.numel()) % 4)])
             fg_frames = T
+        fg_u8 = fg_u8.to(dev, non_blocking=True)
+        if fg_geom is not None and dense is not None:
+            return torch.ops.bgdebias.bgmix_resize_blend(fg_u8, fg_geom, int(fg_frames), th, tw, dense, rows, top, left, app, lut,
+                                                         mean_t, std_t, float(self.alpha), layout)
         if fg_geom is not None:
-            return torch.ops.bgdebias.bgmix_resize_blend(
-                fg_u8.to(dev, non_blocking=True), fg_geom, int(fg_frames), th, tw, pool.tensor,
-                pool.rows(as_dev(bg_idx, torch.int32).clamp_(min=0)), as_dev(bg_top, torch.int32), as_dev(bg_left, torch.int32),
-                as_dev(bg_apply, torch.uint8), lut, torch.tensor(self.bg_mean), torch.tensor(self.bg_std), float(self.alpha),
-                layout)
-        return torch.ops.bgdebias.bgmix_blend(
-            fg_u8.to(dev, non_blocking=True), pool.tensor, pool.rows(as_dev(bg_idx, torch.int32).clamp_(min=0)),
-            as_dev(bg_top, torch.int32), as_dev(bg_left, torch.int32), as_dev(bg_apply, torch.uint8), lut,
-            torch.tensor(self.bg_mean), torch.tensor(self.bg_std), float(self.alpha), layout)
+            fg_u8 = torch.ops.bgdebias.resize_bilinear(fg_u8, fg_geom, int(fg_frames), th, tw)
+        if dense is not None:
+            return torch.ops.bgdebias.bgmix_blend(fg_u8, dense, rows, top, left, app, lut, mean_t, std_t, float(self.alpha), layout)
+        return torch.ops.bgdebias.bgmix_blend_ragged(fg_u8, ragged.data, ragged.slots_tensor, ragged.tables.tensor, rows, top, left,
+                                                     app, lut, mean_t, std_t, float(self.alpha), layout)
+
+    def _aa_tables(self) -> AATables:
+        if "aa_tables" not in self._resized_cache:
+            self._resized_cache["aa_tables"] = AATables(self.device)
+        return self._resized_cache["aa_tables"]
 
     def _lut(self, mean, std) -> torch.Tensor:
         key = ("lut", mean, std)
@@ -393,6 +431,14 @@ class BackgroundMixDataset(_Base):
             'bg_left': torch.tensor([int(s['bg_left']) for s in samples], dtype=torch.int32),
             'bg_apply': torch.tensor([int(s['bg_apply']) for s in samples], dtype=torch.uint8),
         })
+        if any('bg_img' in s for s in samples):
+            # random-frame mode: the frames the batch drew are its pool; unmixed samples point at frame 0 and are ignored
+            out['bg_imgs'] = [torch.as_tensor(s['bg_img']) for s in samples if 'bg_img' in s]
+            slot, nxt = [], 0
+            for s in samples:
+                slot.append(nxt if 'bg_img' in s else 0)
+                nxt += 'bg_img' in s
+            out['bg_slot'] = torch.tensor(slot, dtype=torch.int32)
         if 'label' in samples[0]:
             out['label'] = torch.stack([torch.as_tensor(s['label']) for s in samples])
         if 'randAug' in samples[0]:
@@ -403,10 +449,19 @@ class BackgroundMixDataset(_Base):
         """The GPU half of the ``device_mix=True`` path: turns a :meth:`host_collate` batch into the dict the
         reference's default_collate would hand the model (``imgs`` fp32 ``[B,T,3,H,W]`` on the device, ``label``,
         ``randAug``, ``bg_idx``) with one fused launch."""
-        out = {k: v for k, v in batch.items() if k not in ('imgs', 'bg_top', 'bg_left', 'bg_apply', 'fg_geom', 'fg_frames')}
-        out['imgs'] = self.mix_batch_on_device(batch['imgs'], batch['bg_idx'], batch['bg_top'], batch['bg_left'],
-                                               batch['bg_apply'], layout=layout, fg_geom=batch.get('fg_geom'),
-                                               fg_frames=batch.get('fg_frames'))
+        out = {k: v for k, v in batch.items()
+               if k not in ('imgs', 'bg_top', 'bg_left', 'bg_apply', 'fg_geom', 'fg_frames', 'bg_imgs', 'bg_slot')}
+        if self.back_ground_from_bg_dir or 'bg_imgs' in batch:
+            out['imgs'] = self.mix_batch_on_device(batch['imgs'], batch['bg_idx'], batch['bg_top'], batch['bg_left'],
+                                                   batch['bg_apply'], layout=layout, fg_geom=batch.get('fg_geom'),
+                                                   fg_frames=batch.get('fg_frames'), bg_imgs=batch.get('bg_imgs'),
+                                                   bg_slot=batch.get('bg_slot'))
+        else:                                             # random-frame mode and no sample of the batch was mixed
+            out['imgs'] = self.mix_batch_on_device(batch['imgs'], batch['bg_idx'], batch['bg_top'], batch['bg_left'],
+                                                   batch['bg_apply'], layout=layout, fg_geom=batch.get('fg_geom'),
+                                                   fg_frames=batch.get('fg_frames'),
+                                                   bg_imgs=[torch.zeros((3, *self.bg_crop_size), dtype=torch.uint8)],
+                                                   bg_slot=torch.zeros(len(batch['bg_idx']), dtype=torch.int32))
         return out
 
     def gpu_collate(self, samples: List[dict]) -> dict:

@@ -77,30 +77,65 @@ int current_device_props(DeviceProps *out)
 }
 
 // ---- workspace --------------------------------------------------------------------------------
+void Workspace::free_all()
+{
+    // at thread exit the context may already be gone (process teardown): errors are ignored, nothing is reported
+    for (Slot &s : ring) {
+        if (s.d_ptr) cudaFree(s.d_ptr);
+        if (s.h_pinned) cudaFreeHost(s.h_pinned);
+        if (s.ready) cudaEventDestroy(s.ready);
+        s = Slot{};
+    }
+    cudaGetLastError();
+    d_ptr = h_pinned = nullptr;
+    bytes = 0;
+}
+
 int Workspace::acquire(size_t need)
 {
     int dev = 0;
     BGD_CUDA_TRY(cudaGetDevice(&dev));
-    if (ready) BGD_CUDA_TRY(cudaEventSynchronize(ready));   // previous upload consumed
-    if (dev != device || need > bytes) {
-        if (d_ptr) cudaFree(d_ptr);
-        if (h_pinned) cudaFreeHost(h_pinned);
-        d_ptr = h_pinned = nullptr;
-        bytes = 0;
+    if (dev != device) {                       // buffers AND events belong to the device they were created on
+        if (device >= 0) {
+            int back = dev;
+            cudaSetDevice(device);
+            free_all();
+            cudaSetDevice(back);
+        }
+        device = dev;
+    }
+    cur = next;
+    next = (next + 1) % kRing;
+    Slot &s = ring[cur];
+    if (s.in_flight) {
+        BGD_CUDA_TRY(cudaEventSynchronize(s.ready));   // the call kRing calls ago has consumed its tables
+        s.in_flight = false;
+    }
+    if (need > s.bytes) {
+        if (s.d_ptr) cudaFree(s.d_ptr);
+        if (s.h_pinned) cudaFreeHost(s.h_pinned);
+        s.d_ptr = s.h_pinned = nullptr;
+        s.bytes = 0;
         size_t cap = std::max<size_t>(need, 1 << 16);
         cap = (cap + 4095) & ~(size_t)4095;
-        BGD_CUDA_TRY(cudaMalloc(&d_ptr, cap));
-        BGD_CUDA_TRY(cudaMallocHost(&h_pinned, cap));
-        bytes = cap;
-        device = dev;
-        if (!ready) BGD_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        BGD_CUDA_TRY(cudaMalloc(&s.d_ptr, cap));
+        BGD_CUDA_TRY(cudaMallocHost(&s.h_pinned, cap));
+        s.bytes = cap;
     }
+    if (!s.ready) BGD_CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+    d_ptr = s.d_ptr;
+    h_pinned = s.h_pinned;
+    bytes = s.bytes;
     return BGD_OK;
 }
 
 int Workspace::release(cudaStream_t stream)
 {
-    if (ready) BGD_CUDA_TRY(cudaEventRecord(ready, stream));
+    Slot &s = ring[cur];
+    if (s.ready) {
+        BGD_CUDA_TRY(cudaEventRecord(s.ready, stream));
+        s.in_flight = true;
+    }
     return BGD_OK;
 }
 
@@ -139,26 +174,46 @@ static int median_varlen_dispatch(const uint8_t *d_frames, const int64_t *h_offs
                     (long long)T_max, (long long)N);
     // AUTO / LDSM: videos of up to 512 frames take the transposing-load kernel, longer ones the column-plane kernel
     if (variant == BGD_MEDIAN_COLPLANE || variant == BGD_MEDIAN_LDSM || (variant == BGD_MEDIAN_AUTO && can_col))
-        return median_tma_varlen(d_frames, h_offsets, V, N, d_out, variant != BGD_MEDIAN_COLPLANE, stream);
-    if (variant == BGD_MEDIAN_BITSLICED || (variant == BGD_MEDIAN_AUTO && can_bit))
-        return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
-
-    // generic variant: tables row0[V] | T[V]; grid.y carries the video index, 65535 per launch
-    Workspace &ws = thread_workspace();
-    if (int rc = ws.acquire((size_t)V * 12)) return rc;
-    int64_t *h_row0 = static_cast<int64_t *>(ws.h_pinned);
-    int32_t *h_T = reinterpret_cast<int32_t *>(h_row0 + V);
-    for (int64_t v = 0; v < V; ++v) {
-        h_row0[v] = h_offsets[v];
-        h_T[v] = (int32_t)(h_offsets[v + 1] - h_offsets[v]);
+        return median_tma_varlen(d_frames, h_offsets, V, N, d_out, variant != BGD_MEDIAN_COLPLANE, nullptr, 0, stream);
+    // AUTO with SOME videos beyond the TMA kernels' frame limit (the rawframes variant has no frame cap,
+    // comix_loader.py:157-161): those videos alone take the generic kernel, the rest of the batch keeps the fast path
+    std::vector<int64_t> fast, slow;
+    if (variant == BGD_MEDIAN_AUTO && aligned && median_tma_supports(1, N)) {
+        for (int64_t v = 0; v < V; ++v)
+            (median_tma_supports(h_offsets[v + 1] - h_offsets[v], N) ? fast : slow).push_back(v);
     }
-    BGD_CUDA_TRY(cudaMemcpyAsync(ws.d_ptr, ws.h_pinned, (size_t)V * 12, cudaMemcpyHostToDevice, stream));
+    if (!fast.empty()) {
+        if (int rc = median_tma_varlen(d_frames, h_offsets, V, N, d_out, true, fast.data(), (int64_t)fast.size(), stream)) return rc;
+        if (slow.empty()) return BGD_OK;
+    } else if (variant == BGD_MEDIAN_BITSLICED || (variant == BGD_MEDIAN_AUTO && can_bit)) {
+        return median_bitsliced_varlen(d_frames, h_offsets, V, N, d_out, stream);
+    } else {
+        slow.resize((size_t)V);
+        for (int64_t v = 0; v < V; ++v) slow[(size_t)v] = v;
+    }
+
+    // generic variant: tables row0[n] | T[n] for the videos in `slow`; grid.y carries the position in a run of
+    // consecutive videos, 65535 per launch
+    const int64_t n = (int64_t)slow.size();
+    Workspace &ws = thread_workspace();
+    if (int rc = ws.acquire((size_t)n * 12)) return rc;
+    int64_t *h_row0 = static_cast<int64_t *>(ws.h_pinned);
+    int32_t *h_T = reinterpret_cast<int32_t *>(h_row0 + n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = slow[(size_t)i];
+        h_row0[i] = h_offsets[v];
+        h_T[i] = (int32_t)(h_offsets[v + 1] - h_offsets[v]);
+    }
+    BGD_CUDA_TRY(cudaMemcpyAsync(ws.d_ptr, ws.h_pinned, (size_t)n * 12, cudaMemcpyHostToDevice, stream));
     const int64_t *d_row0 = static_cast<const int64_t *>(ws.d_ptr);
-    const int32_t *d_T = reinterpret_cast<const int32_t *>(d_row0 + V);
+    const int32_t *d_T = reinterpret_cast<const int32_t *>(d_row0 + n);
     int rc = BGD_OK;
-    for (int64_t v0 = 0; v0 < V && rc == BGD_OK; v0 += 65535) {
-        const int64_t nv = std::min<int64_t>(65535, V - v0);
-        rc = launch_median_swar(d_frames, d_row0 + v0, d_T + v0, nv, N, d_out + v0 * N, (int)std::min<int64_t>(T_max, 1 << 30), stream);
+    for (int64_t i0 = 0; i0 < n && rc == BGD_OK;) {
+        int64_t i1 = i0 + 1;                                   // a run of consecutive videos shares a launch
+        int32_t run_T = h_T[i0];
+        while (i1 < n && i1 - i0 < 65535 && slow[(size_t)i1] == slow[(size_t)i1 - 1] + 1) run_T = std::max(run_T, h_T[i1++]);
+        rc = launch_median_swar(d_frames, d_row0 + i0, d_T + i0, i1 - i0, N, d_out + slow[(size_t)i0] * N, (int)run_T, stream);
+        i0 = i1;
     }
     const int rc2 = ws.release(stream);
     return rc ? rc : rc2;
@@ -179,6 +234,12 @@ struct Stager {
     int device = -1;
 
     size_t h_in_cap = 0, h_out_cap = 0;
+
+    ~Stager()
+    {
+        release_all();                       // at thread exit; errors (context already gone) are ignored
+        cudaGetLastError();
+    }
 
     // device slabs of in_bytes / out_bytes; pinned mirrors only as large as asked (0 = caller's memory is pinned)
     int ensure(int dev, size_t in_bytes, size_t out_bytes, size_t h_in_bytes = (size_t)-1, size_t h_out_bytes = (size_t)-1)
@@ -494,6 +555,43 @@ int bgd_bgmix_blend_normfg_f32(const float *d_fg_norm, int64_t B, int64_t T, int
     if (!d_fg_norm) return fail(BGD_ERR_INVALID, "bgmix: null foreground");
     return launch_bgmix(nullptr, d_fg_norm, B, T, H, W, d_bg_pool, pool_is_u8 != 0, P, Hb, Wb, d_bg_idx, d_top, d_left,
                         d_apply, nullptr, h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_aa_resize_table(int64_t in_size, int64_t out_size, int32_t *taps, int32_t *h_words, int64_t cap_words)
+{
+    return aa_resize_table(in_size, out_size, taps, h_words, cap_words);
+}
+
+int bgd_aa_resize_u8_f32(const uint8_t *d_pool, const bgd_ragged_slot *h_slot, const int32_t *d_tables, float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    return launch_aa_resize(d_pool, h_slot, d_tables, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_bgmix_blend_ragged_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W, const uint8_t *d_pool,
+                               const bgd_ragged_slot *d_slots, int64_t P, const int32_t *d_tables, const int32_t *d_bg_idx,
+                               const int32_t *d_top, const int32_t *d_left, const uint8_t *d_apply, const float *d_fg_lut,
+                               const float *h_bg_mean, const float *h_bg_std, double alpha, int layout, float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    if (!d_fg) return fail(BGD_ERR_INVALID, "bgmix (ragged): null foreground");
+    return launch_bgmix_ragged(d_fg, nullptr, B, T, H, W, d_pool, d_slots, P, d_tables, d_bg_idx, d_top, d_left, d_apply, d_fg_lut,
+                               h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int bgd_bgmix_blend_ragged_normfg_f32(const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W, const uint8_t *d_pool,
+                                      const bgd_ragged_slot *d_slots, int64_t P, const int32_t *d_tables,
+                                      const int32_t *d_bg_idx, const int32_t *d_top, const int32_t *d_left,
+                                      const uint8_t *d_apply, const float *h_bg_mean, const float *h_bg_std, double alpha,
+                                      int layout, float *d_out, void *stream)
+{
+    DeviceProps dp;
+    if (int rc = current_device_props(&dp)) return rc;
+    if (!d_fg_norm) return fail(BGD_ERR_INVALID, "bgmix (ragged): null foreground");
+    return launch_bgmix_ragged(nullptr, d_fg_norm, B, T, H, W, d_pool, d_slots, P, d_tables, d_bg_idx, d_top, d_left, d_apply,
+                               nullptr, h_bg_mean, h_bg_std, alpha, layout, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int bgd_resize_bilinear_u8(const uint8_t *d_src, int64_t src_bytes, const int64_t *h_geom, int64_t B, int64_t T, int64_t H,

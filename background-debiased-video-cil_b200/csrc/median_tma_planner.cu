@@ -96,9 +96,11 @@ bool median_tma_supports(int64_t T_max, int64_t N)
 }
 
 int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t V, int64_t N, uint8_t *d_out,
-                           bool use_ldsm, cudaStream_t stream)
+                           bool use_ldsm, const int64_t *subset, int64_t n_subset, cudaStream_t stream)
 {
     if (V == 0 || N == 0) return BGD_OK;
+    if (subset && n_subset == 0) return BGD_OK;
+    const int64_t n_vid = subset ? n_subset : V;
     DeviceProps dp;
     if (int rc = current_device_props(&dp)) return rc;
     const Tuning tn = read_tuning();
@@ -109,7 +111,8 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
     if (row_hi - row_lo >= ((int64_t)1 << 31)) return fail(BGD_ERR_UNSUPPORTED, "median: more than 2^31 rows per call");
     std::map<Key, std::vector<int64_t>> classes;
     bool any_ldsm = false, any_col = false;
-    for (int64_t v = 0; v < V; ++v) {
+    for (int64_t i = 0; i < n_vid; ++i) {
+        const int64_t v = subset ? subset[i] : i;
         Key k;
         if (!classify((int)(h_offsets[v + 1] - h_offsets[v]), tn, use_ldsm, &k))
             return fail(BGD_ERR_UNSUPPORTED, "median (column-plane): video %lld has too many frames", (long long)v);
@@ -146,14 +149,14 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
 
     // one table upload for all classes: row0[V] | out[V] | T[V], in class order
     Workspace &ws = thread_workspace();
-    const size_t tbl_bytes = (size_t)V * (8 + 8 + 4);
+    const size_t tbl_bytes = (size_t)n_vid * (8 + 8 + 4);
     if (int rc = ws.acquire(tbl_bytes)) return rc;
     int64_t *h_row0 = static_cast<int64_t *>(ws.h_pinned);
-    int64_t *h_out = h_row0 + V;
-    int32_t *h_T = reinterpret_cast<int32_t *>(h_out + V);
+    int64_t *h_out = h_row0 + n_vid;
+    int32_t *h_T = reinterpret_cast<int32_t *>(h_out + n_vid);
     const int64_t *d_row0 = static_cast<const int64_t *>(ws.d_ptr);
-    const int64_t *d_outi = d_row0 + V;
-    const int32_t *d_T = reinterpret_cast<const int32_t *>(d_outi + V);
+    const int64_t *d_outi = d_row0 + n_vid;
+    const int32_t *d_T = reinterpret_cast<const int32_t *>(d_outi + n_vid);
     {
         int64_t pos = 0;
         for (auto &kv : classes)

@@ -141,8 +141,8 @@ def temporal_median_frames(frames: List[np.ndarray], device=0) -> np.ndarray:
     ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     out = np.empty(shape, np.uint8)
     dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
-    _cabi.check(_cabi.lib().bgd_temporal_median_u8_host(ptrs, len(arrs), N, out.ctypes.data,
-                                                        dev.index if dev.index is not None else 0))
+    index = dev.index if dev.index is not None else torch.cuda.current_device()      # 'cuda' = the current device
+    _cabi.check(_cabi.lib().bgd_temporal_median_u8_host(ptrs, len(arrs), N, out.ctypes.data, index))
     return out
 
 
@@ -217,11 +217,15 @@ def bg_extract_multiple(paths: List[pathlib.Path], output_dir: pathlib.Path, fro
     torch.cuda.set_device(dev)
 
     os.environ.setdefault("OPENCV_FFMPEG_THREADS", "1")     # many videos in flight: one FFmpeg thread per capture, no oversubscription
-    with ThreadPoolExecutor(max_workers=max(1, decode_threads)) as pool:
+    n_dec = max(1, decode_threads)
+    # JPEGs are encoded by their own small pool, so a background reaches the disk as soon as its slab is reduced: the
+    # skip-if-exists resume (and a kill mid-shard) then find the finished part, and host memory holds the backgrounds of
+    # a few slabs instead of the whole shard.  Decodes are submitted in a sliding window for the same reason.
+    with ThreadPoolExecutor(max_workers=n_dec) as pool, ThreadPoolExecutor(max_workers=max(1, min(4, n_dec // 4))) as writers:
         writes = []
 
         def write(tag, bg):                                  # JPEG encoding off the staging path
-            writes.append(pool.submit(cv2.imwrite, str(tag), bg))
+            writes.append(writers.submit(cv2.imwrite, str(tag), bg))
 
         stager = FrameStager(write, dev, slab_mb)
 
@@ -236,7 +240,20 @@ def bg_extract_multiple(paths: List[pathlib.Path], output_dir: pathlib.Path, fro
             except Exception as e:  # keep going, report at the end
                 return str(p), repr(e)
 
-        failures = [f for f in pool.map(decode, paths) if f is not None]
+        failures, window, it = [], [], iter(paths)
+        while True:
+            while len(window) < 4 * n_dec:
+                nxt = next(it, None)
+                if nxt is None:
+                    break
+                window.append(pool.submit(decode, nxt))
+            if not window:
+                break
+            r = window.pop(0).result()
+            if r is not None:
+                failures.append(r)
+            while writes and writes[0].done():
+                writes.pop(0).result()                       # surface write errors early, keep the list short
         stager.flush()
         for w in writes:
             w.result()

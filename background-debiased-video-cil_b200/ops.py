@@ -15,6 +15,9 @@ built library (``ImportError`` otherwise).  Ops are stream-ordered and never syn
                           Tensor apply, Tensor fg_lut, Tensor bg_mean, Tensor bg_std,
                           float alpha, str layout) -> Tensor
         the batched form of BackgroundMixDataset._mix_background (libs/loader/comix_loader.py:138-145).
+    bgdebias::bgmix_blend_ragged(Tensor fg, Tensor pool_bytes, Tensor slots, Tensor tables, <bgmix_blend arguments>) -> Tensor
+        the same blend over a ragged uint8 pool (images of any sizes, or the random frames of comix_loader.py:133-136),
+        with Resize(bg_resize) (comix_loader.py:72; torchvision's antialiased bilinear, bit-exact) inside the launch.
     bgdebias::resize_bilinear(Tensor src, Tensor geom, int T, int H, int W) -> Tensor
     bgdebias::bgmix_resize_blend(Tensor src, Tensor geom, int T, int H, int W, <bgmix_blend arguments>) -> Tensor
         the pipeline's Resize((W, H), keep_ratio=False) (config ..._bgmix_plus_randAug.py:136; cv2 INTER_LINEAR, bit-exact)
@@ -219,6 +222,78 @@ def _(fg, bg_pool, bg_idx, top, left, apply, fg_lut, bg_mean, bg_std, alpha, lay
     B, T, H, W, _ = fg.shape
     shape = (B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W)
     return fg.new_empty(shape, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------- #
+# BG-mix over a ragged uint8 pool (pool.RaggedPool): Resize + RandomCrop + Normalize + blend in one launch
+# --------------------------------------------------------------------------- #
+def _check_ragged(name, B, dev, pool_bytes, slots, tables, bg_idx, top, left, apply):
+    _require(pool_bytes.dtype == torch.uint8 and pool_bytes.dim() == 1, f"{name}: pool_bytes must be a flat uint8 buffer")
+    _require(slots.dtype == torch.uint8 and slots.dim() == 1 and slots.numel() % 40 == 0 and slots.numel() > 0,
+             f"{name}: slots must be the uint8 view of a bgd_ragged_slot table (40 bytes per image)")
+    _require(tables.dtype == torch.int32 and tables.dim() == 1, f"{name}: tables must be int32")
+    for nm, t, dt in (("bg_idx", bg_idx, torch.int32), ("top", top, torch.int32), ("left", left, torch.int32),
+                      ("apply", apply, torch.uint8)):
+        _require(t.dtype == dt and t.dim() == 1 and t.shape[0] == B and t.device == dev, f"{name}: {nm} must be {dt} [B] on {dev}")
+    for nm, t in (("pool_bytes", pool_bytes), ("slots", slots), ("tables", tables)):
+        _require(t.device == dev, f"{name}: {nm} must be on {dev}")
+    _require(slots.data_ptr() % 8 == 0, f"{name}: slots must be 8-byte aligned")
+
+
+@torch.library.custom_op("bgdebias::bgmix_blend_ragged", mutates_args=(), device_types="cuda")
+def bgmix_blend_ragged(fg: torch.Tensor, pool_bytes: torch.Tensor, slots: torch.Tensor, tables: torch.Tensor,
+                       bg_idx: torch.Tensor, top: torch.Tensor, left: torch.Tensor, apply: torch.Tensor,
+                       fg_lut: torch.Tensor, bg_mean: torch.Tensor, bg_std: torch.Tensor, alpha: float, layout: str) -> torch.Tensor:
+    _require(fg.dtype == torch.uint8 and fg.dim() == 5 and fg.shape[-1] == 3, "bgmix_blend_ragged: fg must be uint8 [B, T, H, W, 3]")
+    _require(layout in _cabi.LAYOUTS, f"bgmix_blend_ragged: layout must be one of {sorted(_cabi.LAYOUTS)}")
+    B, T, H, W, _ = fg.shape
+    dev = fg.device
+    _check_ragged("bgmix_blend_ragged", B, dev, pool_bytes, slots, tables, bg_idx, top, left, apply)
+    _require(fg_lut.dtype == torch.float32 and tuple(fg_lut.shape) == (3, 256) and fg_lut.device == dev,
+             "bgmix_blend_ragged: fg_lut must be float32 [3, 256] on the device")
+    fg = fg.contiguous()
+    bg_idx, top, left, apply, fg_lut, pool_bytes, slots, tables = (x.contiguous() for x in (bg_idx, top, left, apply, fg_lut, pool_bytes, slots, tables))
+    out = torch.empty((B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().bgd_bgmix_blend_ragged_f32(
+            fg.data_ptr(), B, T, H, W, pool_bytes.data_ptr(), slots.data_ptr(), slots.numel() // 40, tables.data_ptr(),
+            bg_idx.data_ptr(), top.data_ptr(), left.data_ptr(), apply.data_ptr(), fg_lut.data_ptr(), _host3(bg_mean, "bg_mean"),
+            _host3(bg_std, "bg_std"), float(alpha), _cabi.LAYOUTS[layout], out.data_ptr(), _stream_ptr(dev)))
+    return out
+
+
+@bgmix_blend_ragged.register_fake
+def _(fg, pool_bytes, slots, tables, bg_idx, top, left, apply, fg_lut, bg_mean, bg_std, alpha, layout):
+    B, T, H, W, _ = fg.shape
+    return fg.new_empty((B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W), dtype=torch.float32)
+
+
+@torch.library.custom_op("bgdebias::bgmix_blend_ragged_normfg", mutates_args=(), device_types="cuda")
+def bgmix_blend_ragged_normfg(fg_norm: torch.Tensor, pool_bytes: torch.Tensor, slots: torch.Tensor, tables: torch.Tensor,
+                              bg_idx: torch.Tensor, top: torch.Tensor, left: torch.Tensor, apply: torch.Tensor,
+                              bg_mean: torch.Tensor, bg_std: torch.Tensor, alpha: float, layout: str) -> torch.Tensor:
+    """Ragged-pool blend for a foreground that is already normalised (fp32 ``[B, T, 3, H, W]``)."""
+    _require(fg_norm.dtype == torch.float32 and fg_norm.dim() == 5 and fg_norm.shape[2] == 3,
+             "bgmix_blend_ragged_normfg: fg_norm must be float32 [B, T, 3, H, W]")
+    _require(layout in _cabi.LAYOUTS, f"bgmix_blend_ragged_normfg: layout must be one of {sorted(_cabi.LAYOUTS)}")
+    B, T, _, H, W = fg_norm.shape
+    dev = fg_norm.device
+    _check_ragged("bgmix_blend_ragged_normfg", B, dev, pool_bytes, slots, tables, bg_idx, top, left, apply)
+    fg_norm = fg_norm.contiguous()
+    bg_idx, top, left, apply, pool_bytes, slots, tables = (x.contiguous() for x in (bg_idx, top, left, apply, pool_bytes, slots, tables))
+    out = torch.empty((B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().bgd_bgmix_blend_ragged_normfg_f32(
+            fg_norm.data_ptr(), B, T, H, W, pool_bytes.data_ptr(), slots.data_ptr(), slots.numel() // 40, tables.data_ptr(),
+            bg_idx.data_ptr(), top.data_ptr(), left.data_ptr(), apply.data_ptr(), _host3(bg_mean, "bg_mean"),
+            _host3(bg_std, "bg_std"), float(alpha), _cabi.LAYOUTS[layout], out.data_ptr(), _stream_ptr(dev)))
+    return out
+
+
+@bgmix_blend_ragged_normfg.register_fake
+def _(fg_norm, pool_bytes, slots, tables, bg_idx, top, left, apply, bg_mean, bg_std, alpha, layout):
+    B, T, _, H, W = fg_norm.shape
+    return fg_norm.new_empty((B, T, 3, H, W) if layout == "NTCHW" else (B, 3, T, H, W))
 
 
 # --------------------------------------------------------------------------- #

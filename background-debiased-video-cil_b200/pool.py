@@ -9,9 +9,13 @@ the pool is index ``i`` of ``bg_files`` -- the reference's ``bg_idx``.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
+
+SLOT_DTYPE = np.dtype([("offset", "<i8"), ("h", "<i4"), ("w", "<i4"), ("Hb", "<i4"), ("Wb", "<i4"),
+                       ("xtab", "<i4"), ("ytab", "<i4"), ("kx", "<i4"), ("ky", "<i4")])   # bgd_ragged_slot, 40 bytes
 
 
 def resized_hw(h: int, w: int, size: int) -> tuple:
@@ -45,19 +49,153 @@ def _map_in_order(fn, items, workers: Optional[int] = None) -> list:
         return list(ex.map(fn, items))
 
 
+class AATables:
+    """Weight tables of torchvision's antialiased bilinear ``Resize`` (ATen's separable CPU kernel), one per distinct
+    ``(in_size, out_size)``, evaluated on the host by ``bgd_aa_resize_table`` and kept in one int32 device tensor."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._host: List[np.ndarray] = []
+        self._where: Dict[Tuple[int, int], Tuple[int, int]] = {}
+        self._words = 0
+        self._dev: Optional[torch.Tensor] = None
+
+    def lookup(self, in_size: int, out_size: int) -> Tuple[int, int]:
+        """(word offset, taps) of the table for this axis; (-1, 0) when the size does not change (the pass is skipped)."""
+        if in_size == out_size:
+            return -1, 0
+        key = (int(in_size), int(out_size))
+        if key not in self._where:
+            import ctypes
+            from . import _cabi
+            taps = ctypes.c_int32()
+            _cabi.check(_cabi.lib().bgd_aa_resize_table(key[0], key[1], ctypes.byref(taps), None, 0))
+            words = np.empty(key[1] * (2 + taps.value), dtype=np.int32)
+            _cabi.check(_cabi.lib().bgd_aa_resize_table(key[0], key[1], ctypes.byref(taps), words.ctypes.data, words.size))
+            self._where[key] = (self._words, int(taps.value))
+            self._host.append(words)
+            self._words += words.size
+            self._dev = None
+        return self._where[key]
+
+    @property
+    def tensor(self) -> torch.Tensor:
+        if self._dev is None:
+            host = np.concatenate(self._host) if self._host else np.zeros(1, np.int32)
+            self._dev = torch.from_numpy(host).to(self.device)
+        return self._dev
+
+
+class RaggedPool:
+    """Backgrounds of ANY sizes, uint8 at native size, in one device byte buffer plus a slot table -- the form
+    ``bgdebias::bgmix_blend_ragged`` reads.  ``Resize(bg_resize)`` (comix_loader.py:72) happens inside the blend launch,
+    so a pool costs ``3*h*w`` bytes per image (Sth-Sth-v2: ~68 GB instead of ~308 GB resized fp32) and images of
+    different widths (HMDB51, Sth-Sth-v2) share one pool, each cropped at its own resized size as the reference does."""
+
+    def __init__(self, bg_resize: Optional[int] = 256, device="cuda", tables: Optional[AATables] = None):
+        self.bg_resize = bg_resize
+        self.device = torch.device(device)
+        self.tables = tables if tables is not None else AATables(self.device)
+        self.data: Optional[torch.Tensor] = None          # uint8 [capacity] on the device
+        self.used = 0                                     # bytes in use
+        self.slots = np.zeros(0, dtype=SLOT_DTYPE)        # host copy of the slot table
+        self._slots_dev: Optional[torch.Tensor] = None
+
+    def __len__(self) -> int:
+        return int(self.slots.shape[0])
+
+    def make_slot(self, offset: int, h: int, w: int) -> np.void:
+        Hb, Wb = (h, w) if self.bg_resize is None else resized_hw(h, w, self.bg_resize)
+        xtab, kx = self.tables.lookup(w, Wb)
+        ytab, ky = self.tables.lookup(h, Hb)
+        return np.array([(offset, h, w, Hb, Wb, xtab, ytab, kx, ky)], dtype=SLOT_DTYPE)[0]
+
+    def append(self, images: Sequence) -> None:
+        """``images``: uint8 ``[3, h, w]`` arrays / tensors (what ``read_image(mode=RGB)`` returns), any sizes."""
+        imgs = []
+        for im in images:
+            t = torch.as_tensor(im)
+            if t.dim() != 3 or t.shape[0] != 3 or t.dtype != torch.uint8:
+                raise ValueError("background images must be uint8 [3, h, w]")
+            imgs.append(t.contiguous())
+        if not imgs:
+            return
+        sizes = [int(t.numel()) for t in imgs]
+        starts = [(o + 15) & ~15 for o in np.cumsum([0] + [(n + 15) & ~15 for n in sizes[:-1]]).tolist()]
+        total = starts[-1] + sizes[-1]
+        base = (self.used + 15) & ~15
+        need = base + total
+        if self.data is None or need > self.data.numel():
+            cap = max(need, 2 * (self.data.numel() if self.data is not None else 0))
+            grown = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            if self.data is not None and self.used:
+                grown[:self.used].copy_(self.data[:self.used])
+            self.data = grown
+        staging = torch.empty(total, dtype=torch.uint8, pin_memory=self.device.type == "cuda")
+        for t, o in zip(imgs, starts):
+            staging[o:o + t.numel()] = t.reshape(-1)
+        self.data[base:base + total].copy_(staging, non_blocking=True)
+        new = np.zeros(len(imgs), dtype=SLOT_DTYPE)
+        for i, (t, o) in enumerate(zip(imgs, starts)):
+            new[i] = self.make_slot(base + o, int(t.shape[1]), int(t.shape[2]))
+        self.slots = np.concatenate([self.slots, new])
+        self.used = need
+        self._slots_dev = None
+
+    @property
+    def slots_tensor(self) -> torch.Tensor:
+        """The slot table as a uint8 device tensor (``len(self) * 40`` bytes)."""
+        if self._slots_dev is None:
+            raw = np.ascontiguousarray(self.slots).view(np.uint8).reshape(-1)
+            self._slots_dev = torch.from_numpy(raw.copy()).to(self.device)
+        return self._slots_dev
+
+    def hw(self, slot: int) -> Tuple[int, int]:
+        """Size of image ``slot`` after Resize -- what RandomCrop draws its offsets from."""
+        s = self.slots[slot]
+        return int(s["Hb"]), int(s["Wb"])
+
+    def uniform_hw(self) -> Optional[Tuple[int, int, int, int]]:
+        """(h, w, Hb, Wb) if every image has the same size, else None."""
+        if not len(self):
+            return None
+        s0 = self.slots[0]
+        same = (self.slots["h"] == s0["h"]).all() and (self.slots["w"] == s0["w"]).all()
+        return (int(s0["h"]), int(s0["w"]), int(s0["Hb"]), int(s0["Wb"])) if same else None
+
+    def resized(self, slot: int) -> torch.Tensor:
+        """fp32 ``[3, Hb, Wb]``: ``Resize(bg_resize)(read_image(...).float())`` of one image, computed on the device."""
+        import ctypes
+        from . import _cabi
+        s = self.slots[slot]
+        out = torch.empty((3, int(s["Hb"]), int(s["Wb"])), dtype=torch.float32, device=self.device)
+        c_slot = _cabi.RaggedSlot(*[int(s[k]) for k in SLOT_DTYPE.names])
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().bgd_aa_resize_u8_f32(self.data.data_ptr(), ctypes.byref(c_slot), self.tables.tensor.data_ptr(),
+                                                         out.data_ptr(), int(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
+
 class BackgroundPool:
     """Backgrounds after ``Resize``, resident on one device.
 
-    ``tensor``: fp32 (or uint8 when built with ``keep_uint8=True`` and no resize) ``[P, 3, Hb, Wb]``.
+    ``tensor``: fp32 (or uint8 when built with ``keep_uint8=True`` and no resize) ``[P, 3, Hb, Wb]``, or ``None`` for a
+    pool that only exists in ragged form (images of several sizes, or too large to keep resized).
+    ``ragged``: the :class:`RaggedPool` behind a :class:`BackgroundStore` view.
     ``names``:  one label per slot (file path or video name), same order as ``bg_files``.
     """
 
-    def __init__(self, tensor: torch.Tensor, names: Sequence[str]):
-        if tensor.dim() != 4 or tensor.shape[1] != 3:
-            raise ValueError("pool tensor must be [P, 3, Hb, Wb]")
-        if len(names) != tensor.shape[0]:
-            raise ValueError("one name per pool slot")
-        self.tensor = tensor
+    def __init__(self, tensor: Optional[torch.Tensor], names: Sequence[str], ragged: Optional["RaggedPool"] = None):
+        if tensor is None and ragged is None:
+            raise ValueError("a pool needs a dense tensor or a ragged store")
+        if tensor is not None:
+            if tensor.dim() != 4 or tensor.shape[1] != 3:
+                raise ValueError("pool tensor must be [P, 3, Hb, Wb]")
+            if len(names) != tensor.shape[0]:
+                raise ValueError("one name per pool slot")
+        self.tensor = tensor                              # dense form, or None: blend from `ragged`
+        self.ragged = ragged                              # uint8 images of any sizes (a store view always has it)
+        self._slots_host: Optional[List[int]] = None
         self.names: List[str] = list(names)
         self.index_names: List[str] = self.names          # pool index i -> name (differs from `names` for a store view)
         self.slots: Optional[torch.Tensor] = None         # int32 [len(index_names)]: pool index -> row of `tensor`; None = identity
@@ -67,7 +205,21 @@ class BackgroundPool:
 
     @property
     def hw(self) -> tuple:
-        return int(self.tensor.shape[2]), int(self.tensor.shape[3])
+        """(Hb, Wb) of a pool whose images all resize to one shape."""
+        if self.tensor is not None:
+            return int(self.tensor.shape[2]), int(self.tensor.shape[3])
+        u = self.ragged.uniform_hw()
+        if u is None:
+            raise ValueError("backgrounds of several sizes: ask hw_of(bg_idx)")
+        return u[2], u[3]
+
+    def hw_of(self, bg_idx: int) -> tuple:
+        """Size after Resize of the image pool index ``bg_idx`` draws -- what RandomCrop.get_params sees
+        (comix_loader.py:73 applied to that image)."""
+        if self.ragged is None:
+            return self.hw
+        slot = self._slots_host[bg_idx] if self._slots_host is not None else bg_idx
+        return self.ragged.hw(slot)
 
     def rows(self, bg_idx: torch.Tensor) -> torch.Tensor:
         """Rows of ``tensor`` for pool indices ``bg_idx`` (int32, on the pool's device)."""
@@ -77,23 +229,28 @@ class BackgroundPool:
 
     @classmethod
     def from_images(cls, images: Sequence, names: Optional[Sequence[str]] = None, bg_resize: Optional[int] = 256,
-                    device="cuda", keep_uint8: bool = False) -> "BackgroundPool":
+                    device="cuda", keep_uint8: bool = False, ragged: Optional[bool] = None) -> "BackgroundPool":
         """``images``: uint8 RGB arrays/tensors ``[3, h, w]`` (what ``read_image(mode=RGB)`` returns).
-        All images must resize to the same ``(Hb, Wb)`` -- true for a dataset of one resolution."""
+
+        Images of one size give a dense pool (resized with torchvision itself on the host); images of several sizes --
+        or ``ragged=True`` -- give a ragged uint8 pool that is resized inside the blend launch."""
         if len(images) == 0:
             raise ValueError("empty background pool")     # reference: torch.randint(0, ...) raises at draw time
-        def prepare(im):
+        tens = []
+        for im in images:
             t = torch.as_tensor(im)
             if t.dim() != 3 or t.shape[0] != 3:
                 raise ValueError("background images must be [3, h, w]")
-            return t.to(torch.uint8) if (keep_uint8 and bg_resize is None) else resize_like_reference(t, bg_resize)
-
-        out = _map_in_order(prepare, images)
-        shapes = {tuple(t.shape) for t in out}
-        if len(shapes) != 1:
-            raise ValueError(f"backgrounds resize to different shapes {sorted(shapes)}; build one pool per shape")
-        pool = torch.stack(out).contiguous()
-        names = list(names) if names is not None else [str(i) for i in range(len(out))]
+            tens.append(t)
+        names = list(names) if names is not None else [str(i) for i in range(len(tens))]
+        if ragged is None:
+            ragged = len({tuple(t.shape) for t in tens}) != 1
+        if ragged:
+            rp = RaggedPool(bg_resize, device)
+            rp.append([t.to(torch.uint8) for t in tens])
+            return cls(None, names, ragged=rp)
+        prepare = lambda t: t.to(torch.uint8) if (keep_uint8 and bg_resize is None) else resize_like_reference(t, bg_resize)  # noqa: E731
+        pool = torch.stack(_map_in_order(prepare, tens)).contiguous()
         return cls(pool.to(device, non_blocking=True), names)
 
     @classmethod
@@ -160,27 +317,43 @@ class BackgroundStore:
     The reference's trainer rewrites ``dataset.bg_files`` between CIL tasks -- ``keep_all_backgrounds``
     (libs/cil/cil.py:193-195,690-694), ``cbf_full_bg`` (:146-160) and ``merge_bg_files`` (:390-393) are
     unions / extensions of path lists -- and every sample then decodes its background again.  Here each
-    path is decoded + resized once, the pixels stay in one ``[capacity, 3, Hb, Wb]`` tensor, and a pool is
-    an int32 slot table over it: set operations on the path lists never copy or re-decode pixels, and
-    duplicates in ``bg_files`` (``extend`` creates them) share a slot and keep their draw probability.
+    path is decoded once and stays on the device as uint8 at its native size (:class:`RaggedPool`: any mix of
+    sizes, ``Resize`` evaluated inside the blend launch); a pool is an int32 slot table over the store, so set
+    operations on the path lists never copy or re-decode pixels, and duplicates in ``bg_files`` (``extend``
+    creates them) share a slot and keep their draw probability.
+
+    When every image has the same size and the resized fp32 copy fits ``dense_budget_bytes`` (default: a quarter
+    of the device's memory), :attr:`tensor` additionally caches ``Resize(bg_resize)`` of every image as fp32
+    ``[n, 3, Hb, Wb]`` -- computed on the device by the same arithmetic -- and the blend reads that instead
+    (one load per value instead of a 2x2..3x3 tap window).  Both forms give identical bits.
     """
 
-    def __init__(self, bg_resize: Optional[int] = 256, device="cuda", keep_uint8: bool = False):
+    def __init__(self, bg_resize: Optional[int] = 256, device="cuda", keep_uint8: bool = False,
+                 dense_budget_bytes: Optional[int] = None):
         self.bg_resize = bg_resize
         self.device = torch.device(device)
-        self.keep_uint8 = keep_uint8
-        self.tensor: Optional[torch.Tensor] = None        # [capacity, 3, Hb, Wb]
+        self.keep_uint8 = keep_uint8                      # dense cache as uint8 (only without a resize)
+        self.ragged = RaggedPool(bg_resize, self.device)
         self.slot_of: dict = {}                           # name -> slot
         self.decoded = 0                                  # images decoded so far (what a rebuild would repeat)
+        self.dense_budget_bytes = dense_budget_bytes
+        self._dense: Optional[torch.Tensor] = None        # [capacity, 3, Hb, Wb]
+        self._dense_rows = 0
 
     def __len__(self) -> int:
         return len(self.slot_of)
 
     @property
     def hw(self) -> tuple:
-        if self.tensor is None:
-            raise ValueError("empty background store")
-        return int(self.tensor.shape[2]), int(self.tensor.shape[3])
+        """(Hb, Wb) of a store whose images all have one size."""
+        u = self.ragged.uniform_hw()
+        if u is None:
+            raise ValueError("empty background store" if not len(self) else
+                             "backgrounds of several sizes: ask hw_of(slot)")
+        return u[2], u[3]
+
+    def hw_of(self, slot: int) -> tuple:
+        return self.ragged.hw(slot)
 
     def ensure(self, names: Sequence[str], reader) -> None:
         """Make every name resident; ``reader(name) -> uint8 [3, h, w]`` is called for new names only."""
@@ -191,36 +364,62 @@ class BackgroundStore:
             t = torch.as_tensor(reader(n))
             if t.dim() != 3 or t.shape[0] != 3:
                 raise ValueError("background images must be [3, h, w]")
-            return t.to(torch.uint8) if (self.keep_uint8 and self.bg_resize is None) else resize_like_reference(t, self.bg_resize)
+            return t.to(torch.uint8)
 
         imgs = _map_in_order(prepare, new)
-        shapes = {tuple(t.shape) for t in imgs}
-        if self.tensor is not None:
-            shapes.add(tuple(self.tensor.shape[1:]))
-        if len(shapes) != 1:
-            raise ValueError(f"backgrounds resize to different shapes {sorted(shapes)}; build one pool per shape")
         used = len(self.slot_of)
-        need = used + len(imgs)
-        if self.tensor is None or need > self.tensor.shape[0]:
-            cap = max(need, 2 * (self.tensor.shape[0] if self.tensor is not None else 0))
-            grown = torch.empty((cap,) + tuple(imgs[0].shape), dtype=imgs[0].dtype, device=self.device)
-            if self.tensor is not None and used:
-                grown[:used].copy_(self.tensor[:used])
-            self.tensor = grown
-        self.tensor[used:need].copy_(torch.stack(imgs), non_blocking=True)
+        self.ragged.append(imgs)
         for i, n in enumerate(new):
             self.slot_of[n] = used + i
         self.decoded += len(new)
 
+    def _budget(self) -> int:
+        if self.dense_budget_bytes is not None:
+            return int(self.dense_budget_bytes)
+        if self.device.type == "cuda":
+            return int(torch.cuda.get_device_properties(self.device).total_memory // 4)
+        return 1 << 34
+
+    @property
+    def tensor(self) -> Optional[torch.Tensor]:
+        """Dense cache ``[len(self), 3, Hb, Wb]`` (fp32 after Resize, or uint8 with ``keep_uint8`` and no resize) for a
+        store of one image size within the budget, else ``None`` (the blend then reads the ragged store)."""
+        n = len(self)
+        u = self.ragged.uniform_hw()
+        if u is None or n == 0:
+            self._dense, self._dense_rows = None, 0
+            return None
+        h, w, Hb, Wb = u
+        as_u8 = self.keep_uint8 and self.bg_resize is None
+        if n * 3 * Hb * Wb * (1 if as_u8 else 4) > self._budget():
+            self._dense, self._dense_rows = None, 0
+            return None
+        if self._dense is None or self._dense.shape[0] < n:
+            cap = max(n, 2 * (self._dense.shape[0] if self._dense is not None else 0))
+            grown = torch.empty((cap, 3, Hb, Wb), dtype=torch.uint8 if as_u8 else torch.float32, device=self.device)
+            if self._dense is not None and self._dense_rows:
+                grown[:self._dense_rows].copy_(self._dense[:self._dense_rows])
+            self._dense = grown
+        for slot in range(self._dense_rows, n):
+            s = self.ragged.slots[slot]
+            if (h, w) == (Hb, Wb) or self.device.type != "cuda":
+                raw = self.ragged.data[int(s["offset"]):int(s["offset"]) + 3 * h * w].view(3, h, w)
+                self._dense[slot].copy_(raw if as_u8 else resize_like_reference(raw, None if (h, w) == (Hb, Wb) else self.bg_resize))
+            else:
+                self._dense[slot].copy_(self.ragged.resized(slot))
+        self._dense_rows = n
+        return self._dense[:n]
+
     def view(self, names: Sequence[str]) -> "BackgroundPool":
         """The pool whose index ``i`` is ``names[i]`` (the reference's ``bg_idx``): shares this store's
-        pixels; ``slots`` maps pool index -> row of ``tensor``."""
+        pixels; ``slots`` maps pool index -> store slot."""
         if len(names) == 0:
             raise ValueError("empty background pool")
         missing = [n for n in names if n not in self.slot_of]
         if missing:
             raise KeyError(f"{len(missing)} backgrounds are not resident (first: {missing[0]}); call ensure() first")
-        pool = BackgroundPool(self.tensor[:len(self.slot_of)], list(self.slot_of))
+        pool = BackgroundPool(self.tensor, list(self.slot_of), ragged=self.ragged)
         pool.index_names = list(names)
         pool.slots = torch.tensor([self.slot_of[n] for n in names], dtype=torch.int32, device=self.device)
+        pool._slots_host = [self.slot_of[n] for n in names]
         return pool

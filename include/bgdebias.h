@@ -189,6 +189,52 @@ int bgd_bgmix_blend_f32_host(const uint8_t *h_fg, int64_t B, int64_t T, int64_t 
                              const float *h_bg_std, double alpha, int layout, float *d_out,
                              double *h_checksum, int device);
 
+/* ---- BG-mix over a ragged uint8 pool: Resize + RandomCrop + Normalize + blend ---------------------
+ * Replaces the same reference code as bgd_bgmix_blend_f32 (libs/loader/comix_loader.py:138-145 with the
+ * bg_pipeline of :72-75) for pools the uniform [P][3][Hb][Wb] form cannot hold:
+ *   - backgrounds of different sizes (the reference resizes and crops each image at its own size; the HMDB51 and
+ *     Sth-Sth-v2 pools of configs/HMDB51/bgmix_seed_1000_inc_5_stages_bgmix_plus_randAug.py and
+ *     configs/sth-sthv2/seed_1000_inc_9_stages_bgmix_plus_randAug.py have mixed widths),
+ *   - pools too large to keep resized in fp32 (uint8 at native size is ~4.6x smaller),
+ *   - the random-frame mode of _get_bg_image (:133-136, back_ground_from_bg_dir=False): the frames a batch drew,
+ *     shipped with the batch, are its pool.
+ * d_pool is one byte buffer; image s is planar uint8 [3][h][w] (torchvision.io.read_image's layout) at
+ * d_slots[s].offset.  Resize(bg_resize) is evaluated inside the launch with the arithmetic of torchvision's
+ * antialiased bilinear resize on float tensors (ATen UpSampleKernel.cpp, third-party): per-axis weight tables from
+ * bgd_aa_resize_table, horizontal pass then vertical pass, products and sums rounded as that kernel rounds them
+ * (csrc/raggedmix.cu states the order); an axis whose size does not change has no table (-1) and is skipped. */
+typedef struct bgd_ragged_slot {
+    int64_t offset;      /* bytes from d_pool to the image's first byte */
+    int32_t h, w;        /* stored (native) size */
+    int32_t Hb, Wb;      /* size after Resize; top/left of the crop refer to this image */
+    int32_t xtab, ytab;  /* word offsets of the column / row tables in d_tables; -1 = that axis keeps its size */
+    int32_t kx, ky;      /* taps per entry of those tables */
+} bgd_ragged_slot;
+
+/* HOST function, no device needed: weight table of one axis for in_size -> out_size.  *taps receives K; when h_words is
+ * not NULL it receives out_size entries of (2 + K) 32-bit words: {first source index, tap count, K float weights}. */
+int bgd_aa_resize_table(int64_t in_size, int64_t out_size, int32_t *taps, int32_t *h_words, int64_t cap_words);
+
+/* Resize alone (what Resize(bg_resize) of comix_loader.py:72 returns for read_image(...).float()):
+ * image at d_pool + h_slot->offset -> d_out fp32 [3][Hb][Wb].  h_slot is a HOST pointer. */
+int bgd_aa_resize_u8_f32(const uint8_t *d_pool, const bgd_ragged_slot *h_slot, const int32_t *d_tables,
+                         float *d_out, void *stream);
+
+/* The blend; arguments as bgd_bgmix_blend_f32 except the pool: d_slots [P] (device), d_tables (device). */
+int bgd_bgmix_blend_ragged_f32(const uint8_t *d_fg, int64_t B, int64_t T, int64_t H, int64_t W,
+                               const uint8_t *d_pool, const bgd_ragged_slot *d_slots, int64_t P,
+                               const int32_t *d_tables, const int32_t *d_bg_idx, const int32_t *d_top,
+                               const int32_t *d_left, const uint8_t *d_apply, const float *d_fg_lut,
+                               const float *h_bg_mean, const float *h_bg_std, double alpha, int layout,
+                               float *d_out, void *stream);
+
+/* Same for a foreground that is already normalised (fp32 [B][T][3][H][W], as bgd_bgmix_blend_normfg_f32). */
+int bgd_bgmix_blend_ragged_normfg_f32(const float *d_fg_norm, int64_t B, int64_t T, int64_t H, int64_t W,
+                                      const uint8_t *d_pool, const bgd_ragged_slot *d_slots, int64_t P,
+                                      const int32_t *d_tables, const int32_t *d_bg_idx, const int32_t *d_top,
+                                      const int32_t *d_left, const uint8_t *d_apply, const float *h_bg_mean,
+                                      const float *h_bg_std, double alpha, int layout, float *d_out, void *stream);
+
 /* ---- foreground pipeline tail: Resize -> Normalize -> FormatShape (-> blend) -----------------
  * Replaces the tail of the reference's training pipeline
  *   dict(type='Resize', scale=(224, 224), keep_ratio=False), Normalize, FormatShape('NCHW')

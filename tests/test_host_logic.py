@@ -197,8 +197,13 @@ def test_background_store_slots_without_gpu():
     import pytest
     with pytest.raises(KeyError):
         store.view(["n5"])
+    # a second image size is accepted (the reference crops every background at its own size, comix_loader.py:139-141):
+    # the dense cache is gone, sizes are per image
+    store.ensure(["other"], lambda n: torch.zeros(3, 9, 9, dtype=torch.uint8))
+    c = store.view(["other", "n0"])
+    assert c.tensor is None and c.hw_of(0) == (9, 9) and c.hw_of(1) == (8, 10) and len(store) == 5
     with pytest.raises(ValueError):
-        store.ensure(["bad"], lambda n: torch.zeros(3, 9, 9, dtype=torch.uint8))
+        c.hw
 
 
 def _fake_person_detector():
