@@ -325,22 +325,30 @@ class BackgroundMixDataset(_Base):
         return (h, w) if self.bg_resize is None else resized_hw(h, w, self.bg_resize)
 
     def _bg_hw(self, bg_idx: int) -> tuple:
-        """Size after Resize of ``bg_files[bg_idx]`` without touching the GPU: from the resident pool / store when they
-        know the file, else from the image header (cached per path; DataLoader workers take this road)."""
+        """Size after Resize of ``bg_files[bg_idx]``: from the resident pool / store when they know the file; else a
+        process that owns the GPU decodes the image into the store (once), and a forked DataLoader worker reads the image
+        header (cached per path)."""
         if self._pool is not None and tuple(self.bg_files) == self._pool_key:
             return self._pool.hw_of(bg_idx)
         path = self.bg_files[bg_idx]
         if self._store is not None and path in self._store.slot_of:
             return self._store.hw_of(self._store.slot_of[path])
-        if path not in self._resized_cache:
-            if self._bg_reader is not None:
-                img = torch.as_tensor(self._bg_reader(path))
-                h, w = int(img.shape[1]), int(img.shape[2])
-            else:
-                from PIL import Image
-                with Image.open(path) as im:              # header only
-                    w, h = im.size
-            self._resized_cache[path] = self._resized_hw(h, w)
+        if path in self._resized_cache:
+            return self._resized_cache[path]
+        if self.device.type == "cuda" and torch.cuda.is_available() and not torch.cuda._is_in_bad_fork():
+            # a process that may use the GPU decodes the image once, into the store, and reads its size there
+            if self._store is None:
+                self._store = BackgroundStore(self.bg_resize, self.device)
+            self._store.ensure([path], self._read_bg)
+            return self._store.hw_of(self._store.slot_of[path])
+        if self._bg_reader is not None:                   # DataLoader worker: size only, cached per path
+            img = torch.as_tensor(self._bg_reader(path))
+            h, w = int(img.shape[1]), int(img.shape[2])
+        else:
+            from PIL import Image
+            with Image.open(path) as im:                  # header only
+                w, h = im.size
+        self._resized_cache[path] = self._resized_hw(h, w)
         return self._resized_cache[path]
 
     def _pool_hw(self) -> tuple:

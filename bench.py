@@ -39,6 +39,13 @@ WORKLOADS = {
     "sthv2": dict(H=240, W=427, t_lo=24, t_hi=73, t_mul=1, videos=4096, t_text="U[24,72]",
                   label="configs[3]: Sth-Sth-v2-shaped clips, a resident 4,096-clip chunk of the 27,606-clip 1/8 shard"),
 }
+# Legs reported INSIDE the default line under "workloads" (bounded resident chunks, same code path, same run):
+# the other extraction configs of BASELINE.json and the structured-content variant of SURVEY.md section 8d.
+EXTRA_LEGS = {
+    "hmdb51": dict(workload="hmdb51", videos=846, content="random"),
+    "sthv2": dict(workload="sthv2", videos=4096, content="random"),
+    "ucf101_structured": dict(workload="ucf101", videos=416, content="structured"),
+}
 
 
 def _select_workload(name: str) -> None:
@@ -170,6 +177,112 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+
+def fill_frames(frames, Ts, offs, Hh, Ww, content, seed, torch):
+    """Synthetic frames on the device.  "random": uniform bytes (the selection's worst case, every column has T distinct
+    candidates).  "structured": what the temporal median is for -- one static background per video,
+    +-1 sensor noise on 5 % of the samples and a bright 40x40 block that moves a few pixels per frame."""
+    dev = frames.device
+    n_bytes = frames.shape[1]
+    g = torch.Generator(device=dev).manual_seed(seed)
+    rows = frames.shape[0]
+    if content == "random":
+        chunk = max(1, (1 << 30) // n_bytes)
+        for r0 in range(0, rows, chunk):
+            r1 = min(rows, r0 + chunk)
+            frames[r0:r1] = torch.randint(0, 256, (r1 - r0, n_bytes), dtype=torch.uint8, device=dev, generator=g)
+        return
+    for v, T in enumerate(Ts):
+        r0 = int(offs[v])
+        T = int(T)
+        base = torch.randint(40, 200, (1, n_bytes), dtype=torch.int16, device=dev, generator=g)
+        noise = (torch.rand((T, n_bytes), device=dev, generator=g) < 0.05).to(torch.int16) * \
+            (torch.randint(0, 2, (T, n_bytes), dtype=torch.int16, device=dev, generator=g) * 2 - 1)
+        fr = (base + noise).clamp_(0, 255).to(torch.uint8).view(T, Hh, Ww, 3)
+        t = torch.arange(T, device=dev)
+        x0 = (t * 3) % (Ww - 40)
+        y0 = (t * 2) % (Hh - 40)
+        yy = (y0[:, None, None] + torch.arange(40, device=dev)[None, :, None]).expand(T, 40, 40)
+        xx = (x0[:, None, None] + torch.arange(40, device=dev)[None, None, :]).expand(T, 40, 40)
+        tt = t[:, None, None].expand(T, 40, 40)
+        fr[tt, yy, xx] = (255 - (t % 7)).to(torch.uint8)[:, None, None, None].expand(T, 40, 40, 3)
+        frames[r0:r0 + T] = fr.view(T, n_bytes)
+
+
+def spot_check(frames, offs, Ts, out, v_chk, torch):
+    """One video of the timed path against the definition in plain torch: (s[(T-1)//2] + s[T//2]) >> 1 over the sorted column."""
+    sl = slice(int(offs[v_chk]), int(offs[v_chk + 1]))
+    srt = torch.sort(frames[sl].to(torch.int16), dim=0).values
+    Tc = srt.shape[0]
+    return bool(torch.equal(out[v_chk], ((srt[(Tc - 1) // 2] + srt[Tc // 2]) >> 1).to(torch.uint8)))
+
+
+def extraction_leg(leg_name, spec, rank, world, dev, steps, barrier):
+    """One bounded, resident chunk of another extraction workload through the same op: frames/s, roofline, spot check."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bgdebias_b200 import _cabi
+    wl = WORKLOADS[spec["workload"]]
+    Hh, Ww = wl["H"], wl["W"]
+    n_bytes = Hh * Ww * 3
+    V = spec["videos"]
+    rng = np.random.default_rng(50 + rank)
+    Ts = wl["t_mul"] * rng.integers(wl["t_lo"], wl["t_hi"], V)
+    free, _ = torch.cuda.mem_get_info(dev)
+    while int(Ts.sum()) * n_bytes + (4 << 30) > free and V > 16:
+        V //= 2
+        Ts = Ts[:V]
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64))
+    rows = int(offs[-1])
+    frames = torch.empty((rows, n_bytes), dtype=torch.uint8, device=dev)
+    fill_frames(frames, Ts, offs, Hh, Ww, spec["content"], 200 + rank, torch)
+    torch.cuda.synchronize()
+    out = None
+    for _ in range(3):
+        out = torch.ops.bgdebias.temporal_median_varlen(frames, offs)
+    barrier()
+    l0 = _cabi.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = torch.ops.bgdebias.temporal_median_varlen(frames, offs)
+    e1.record()
+    barrier()
+    launches = _cabi.kernel_launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(rows)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t.item()) / steps
+    ok = spot_check(frames, offs, Ts, out, int(np.argmin(Ts)), torch) and spot_check(frames, offs, Ts, out, int(np.argmax(Ts)), torch)
+    step_bytes = (rows + V) * n_bytes
+    peak, _ = measured_peak_gbs()
+    achieved = step_bytes / (ms * 1e-3) / 1e9
+    rec = {"metric": "bg_extraction_frames_per_sec", "value": float(tot.item()) / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+           "steps": steps, "gpu_launches_per_step": launches // steps,
+           "config": {"workload": wl["label"] + f"; resident chunk of {V} videos per GPU, content: {spec['content']}", "videos_per_gpu": V,
+                      "frames_per_gpu": rows, "frame_shape": [Hh, Ww, 3], "T": wl["t_text"], "resident_gb": rows * n_bytes / 1e9},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_step": step_bytes, "traffic": None},
+           "parity_spotcheck": ok}
+    if leg_name == "sthv2" and world > 1:
+        # Sth-Sth-v2's pool (67.9 GB of uint8 backgrounds) is not replicated: the ranks all-gather the INDEX
+        # (name, owner rank, slot on owner) and the pixels stay where they were extracted (SURVEY.md section 8e)
+        from bgdebias_b200.pool import BackgroundPool
+        names = [f"r{rank}_clip{i:06d}" for i in range(V)]
+        BackgroundPool.all_gather_index(names)
+        barrier()
+        t0 = time.perf_counter()
+        index = BackgroundPool.all_gather_index(names)
+        dt = time.perf_counter() - t0
+        rec["index_all_gather"] = {"ms": dt * 1e3, "entries": len(index), "parity": index[rank * V][0] == names[0] and len(index) == world * V}
+    del frames, out
+    torch.cuda.empty_cache()
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -229,11 +342,7 @@ def run_ours(args):
     offs = torch.from_numpy(np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64))
     rows = int(offs[-1])
     frames = torch.empty((rows, N_BYTES), dtype=torch.uint8, device=dev)
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    chunk = max(1, (1 << 30) // N_BYTES)
-    for r0 in range(0, rows, chunk):
-        r1 = min(rows, r0 + chunk)
-        frames[r0:r1] = torch.randint(0, 256, (r1 - r0, N_BYTES), dtype=torch.uint8, device=dev, generator=g)
+    fill_frames(frames, Ts, offs, H, W, args.content, 100 + rank, torch)
     torch.cuda.synchronize()
     step_bytes = (rows + V) * N_BYTES                      # every frame byte read once + one frame written per video
 
@@ -275,12 +384,7 @@ def run_ours(args):
 
     # spot-check the timed path (outside the timed region) against the definition evaluated with plain torch:
     # (s[(T-1)//2] + s[T//2]) >> 1 over the sorted column -- what np.median(...).astype(uint8) gives
-    v_chk = int(np.argmin(Ts))
-    sl = slice(int(offs[v_chk]), int(offs[v_chk + 1]))
-    srt = torch.sort(frames[sl].to(torch.int16), dim=0).values
-    Tc = srt.shape[0]
-    ok = bool(torch.equal(out[v_chk], ((srt[(Tc - 1) // 2] + srt[Tc // 2]) >> 1).to(torch.uint8)))
-    del srt
+    ok = spot_check(frames, offs, Ts, out, int(np.argmin(Ts)), torch) and spot_check(frames, offs, Ts, out, int(np.argmax(Ts)), torch)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     Ve = int(os.environ.get("BGD_BENCH_E2E_VIDEOS", 48))
@@ -488,6 +592,18 @@ def run_ours(args):
     except Exception as e:           # the headline metric stands even if the secondary bench cannot run
         bgmix = {"error": repr(e)}
 
+    # ---- the other extraction configs + structured content, as bounded resident chunks in the same run --------
+    legs = {}
+    if not args.no_legs and WL_NAME == "ucf101":
+        del frames, out, h_frames, h_out
+        torch.cuda.empty_cache()
+        for leg_name, spec in EXTRA_LEGS.items():
+            try:
+                legs[leg_name] = extraction_leg(leg_name, spec, rank, world, dev, max(3, min(args.steps, 8)), barrier)
+            except Exception as e:
+                legs[leg_name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
+
     if rank == 0:
         cb = None
         try:
@@ -516,19 +632,21 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WL["label"], "videos_per_gpu": V,
                        "frames_per_gpu": rows, "frame_shape": [H, W, 3], "T": WL["t_text"], "resident_gb": rows * N_BYTES / 1e9,
-                       "l2": "resident inputs (tens of GB per GPU) exceed L2; no flush needed", "kernel": "median_ldsm for T<=512, median_colplane above (AUTO)",
+                       "l2": "resident inputs (tens of GB per GPU) exceed L2; no flush needed", "kernel": "median_ldsm for T<=512, median_colplane above (AUTO)", "content": args.content,
                        "parallelism": f"shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": rows_e * N_BYTES,
                     "d2h_bytes_per_step": Ve * N_BYTES, "videos_per_step": Ve, "parity": e2e_ok},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": step_bytes,
+                         "traffic": traffic, "traffic_source": "profiles ncu capture (dram bytes per algorithmic byte of one --set full capture) x this step's algorithmic bytes",
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": step_bytes,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cb,
             "clocks": clk.summary(),
             "parity_spotcheck": ok,
             "bgmix": bgmix,
             "pool_all_gather": gather,
+            "workloads": legs,
         })
     if world > 1:
         dist.barrier()
@@ -542,6 +660,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=WL_NAME, choices=sorted(WORKLOADS))
+    ap.add_argument("--content", default="random", choices=["random", "structured"], help="synthetic frame content of the main leg")
+    ap.add_argument("--no-legs", dest="no_legs", action="store_true", help="skip the extra workload legs (hmdb51, sthv2, structured)")
     args = ap.parse_args()
     _select_workload(args.workload)
     if args.impl == "reference":
