@@ -108,6 +108,18 @@ __device__ __forceinline__ uint64_t policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // (a & mask) | (b & ~mask) in one LOP3
 __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t mask)
 {

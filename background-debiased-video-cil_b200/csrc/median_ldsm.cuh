@@ -44,13 +44,22 @@ namespace ldsm {
 constexpr int kStripW = 128;              // bytes per TMA strip (= the 128-byte swizzle span); 2 warps per strip
 constexpr int kMaxStrips = 2;             // a CTA tile is 1 or 2 strips wide
 constexpr int kMaxNH = 16;                // T <= 256: at most 16 half groups (of 16 rows) per column
+#ifndef BGD_LDSM_TWOSEL_MAX
+#define BGD_LDSM_TWOSEL_MAX 4             // even T: two independent selects up to this many plane words per column
+#endif
+#ifndef BGD_LDSM_IMADSTATE_MAX
+#define BGD_LDSM_IMADSTATE_MAX 4          // select state updated by IMAD (not LOP3) up to this many plane words per column
+#endif
 
 struct alignas(64) LParams {
-    CUtensorMap maps[colplane::kNumMaps];  // maps[k]: frames as [rows][N] uint8, box 128 bytes x 2^k rows, SWIZZLE_128B
+    // frames as [rows][N] uint8, SWIZZLE_128B.  Two-column kernels (NH <= 16): maps[j] has a box of 128 bytes x the
+    // j-th frame count of the launch's class (see issue_tile); one-column kernels: maps[k] has a box of 128 bytes x 2^k rows
+    CUtensorMap maps[colplane::kNumMaps];
     uint8_t *out;
     const int64_t *vid_row0;     // [n_videos] first row of each video (relative to the map's base)
     const int32_t *vid_T;        // [n_videos]
     const int64_t *vid_out;      // [n_videos] output slot
+    const uint32_t *vid_mask;    // [n_videos] alive mask of a column's last plane word (rows beyond T are dead)
     int64_t N;
     int64_t num_tiles;
     int32_t tiles_per_video;
@@ -59,6 +68,7 @@ struct alignas(64) LParams {
     int32_t strips;              // strips per CTA tile (1 or 2): tile width = 128 * strips, block = 64 * strips threads
     int32_t stages;              // tile buffers per CTA (ring); tile i of a CTA lives in buffer i % stages
     int32_t max_blocks_per_sm;   // 0 = as many as fit
+    int32_t l2_policy;           // L2 hint of the tensor copies: 0 = evict_first, 1 = evict_normal, 2 = evict_last
 };
 
 int launch(int NH, bool even, const LParams &prm, int sm_count, size_t smem, cudaStream_t stream);
@@ -182,7 +192,11 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     // ~150 instructions of a request are spread evenly instead of making warp 0 the one the others wait for.
     constexpr int kWarps = threads_of<NH, STRIPS>() / 32;
     const bool elected = elect_one();
-    const uint64_t policy = policy_evict_first();
+    // L2 priority of the tensor copies.  Every frame byte is used once, but evict_first is the wrong hint: when frame rows
+    // do not start on 128-byte boundaries (N % 128 != 0, e.g. 240x427x3) neighbouring strips share the sectors at their
+    // common edge, and a line that is dropped at once is fetched twice from HBM (+14..38 % DRAM reads, -17 % speed on the
+    // Sth-Sth-v2 shape); and even for aligned rows the default priority is 1.5-5 % faster (profiles/r2_sweep_l2_policy_*.txt).
+    const uint64_t policy = prm.l2_policy == 0 ? policy_evict_first() : (prm.l2_policy == 2 ? colplane::policy_evict_last() : colplane::policy_evict_normal());
     // Called by all lanes of warp 0 (the table reads are broadcast with SHFL so that ptxas sees warp-uniform
     // TMA operands and moves them to uniform registers without a per-value loop); the producer lane issues.
     auto issue_tile = [&](int vid, int ct, int slot) {
@@ -192,21 +206,30 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         const int row0 = __shfl_sync(0xFFFFFFFFu, (int)prm.vid_row0[vid], 0);
         if (!elected) return;
         mbar_arrive_expect_tx(bar_s, (uint32_t)T * (uint32_t)kTileW);
+        if constexpr (COLS == 2) {
+            // the frame counts of a launch are 16 (NH - 1) + 1 (+ 1 for even T) + 2 j, j = 0..7: maps[j] has a box of
+            // exactly that many rows, so a strip is ONE tensor copy whatever T is
+            const CUtensorMap *map = &prm.maps[(T - (16 * (NH - 1) + 1 + (EVEN ? 1 : 0))) >> 1];
 #pragma unroll
-        for (int s = 0; s < kTileW / kStripW; ++s) {
-            const int col = ct * kTileW + s * kStripW;
-            uint8_t *dst = buf_s + (size_t)s * strip_bytes;
-            int r = 0;
-            while (T - r >= 256) {                       // T = 512 needs two of them
-                tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[8], col, (int)(row0 + r), bar_s, policy);
-                r += 256;
-            }
+            for (int s = 0; s < kTileW / kStripW; ++s)
+                tma_load_2d(buf_s + (size_t)s * strip_bytes, map, ct * kTileW + s * kStripW, row0, bar_s, policy);
+        } else {
 #pragma unroll
-            for (int k = 7; k >= 0; --k)
-                if ((T - r) & (1 << k)) {
-                    tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[k], col, (int)(row0 + r), bar_s, policy);
-                    r += 1 << k;
+            for (int s = 0; s < kTileW / kStripW; ++s) {
+                const int col = ct * kTileW + s * kStripW;
+                uint8_t *dst = buf_s + (size_t)s * strip_bytes;
+                int r = 0;
+                while (T - r >= 256) {                       // T = 512 needs two of them
+                    tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[8], col, (int)(row0 + r), bar_s, policy);
+                    r += 256;
                 }
+#pragma unroll
+                for (int k = 7; k >= 0; --k)
+                    if ((T - r) & (1 << k)) {
+                        tma_load_2d(dst + (size_t)r * kStripW, &prm.maps[k], col, (int)(row0 + r), bar_s, policy);
+                        r += 1 << k;
+                    }
+            }
         }
     };
 
@@ -222,6 +245,7 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     uint32_t phases = 0;                                 // bit s: parity to wait for on bar[s]
     for (; tile < num_tiles; advance(tile, vid, ct)) {
         const int T = prm.vid_T[vid];
+        const uint32_t last_mask = __ldg(prm.vid_mask + vid);
 
         mbar_wait(bar + slot, (phases >> slot) & 1u);
         phases ^= 1u << slot;
@@ -269,21 +293,27 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         }
         if (HALF) bit_transpose8(PS);
 
-        // ---- alive mask of a column's last word: bit 8 y + m is row 32 (NWC-1) + 4 m + y; in the shared
-        //      group column 0 owns bits m < 4 of every byte and column 1 (mask << 4) the bits m >= 4 -------
-        uint32_t last_mask = 0u;
-        {
-            const int n = T - 32 * (NWC - 1);
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                int cnt = (n - y + 3) >> 2;
-                cnt = cnt < 0 ? 0 : (cnt > (HALF ? 4 : 8) ? (HALF ? 4 : 8) : cnt);
-                last_mask |= ((1u << cnt) - 1u) << (8 * y);
-            }
-        }
+        // ---- alive mask of a column's last word (from the per-video table): bit 8 y + m is row 32 (NWC-1) + 4 m + y;
+        //      in the shared group column 0 owns bits m < 4 of every byte and column 1 (mask << 4) the bits m >= 4 -------
 
         // ---- 8-pass MSB-first rank select, per column ------------------------------------------------
+        // State of a select: rc = rank - (number of alive rows), always negative, where rank is the 0-based rank of the
+        // wanted element among the alive rows.  With `ones` alive rows having the bit set, d = rc + ones = rank - zeros
+        // decides the bit (0 iff d < 0); the new rc is d for bit 0 (the zeros stay alive) and rc for bit 1 (rank and the
+        // alive count both drop by zeros), i.e. rc - ones * m0 with m0 = d >> 31: rank itself never has to be kept and
+        // the update is an IMAD.  acc collects  sum_b m_b 2^b  with m_b = -1 where the bit is 0, so the value is 255 + acc.
+        // Everything but the two LOP3 per word and the sign shift runs on the FMA and POPC pipes; the LOP3 pipe is the
+        // one this kernel fills.  Even T runs the select twice, for ranks T/2 - 1 and T/2: two independent chains cost
+        // the LOP3 pipe 4 per word and pass like a shared count with a second set, but no shared-state bookkeeping.
         int med[2] = {0, 0};
+        const int ONE = (int)one, NEG1 = -(int)one, TWO = (int)one << 1;
+        // Few plane words per column (short videos): the per-pass bookkeeping weighs as much as the word work, so it is
+        // kept off the LOP3 pipe entirely -- even T runs two independent selects (ranks T/2 - 1 and T/2: one more POPC
+        // and IMAD per word, no shared-state logic) and rc is updated by IMAD.  Many words per column: issue slots are
+        // what is short, so the two middles share one count until they part and the upper one then follows the
+        // minimum of its own set (an OR over the words instead of a count).
+        constexpr bool kTwoSelects = EVEN && NWC <= BGD_LDSM_TWOSEL_MAX;
+        constexpr bool kImadState = NWC <= BGD_LDSM_IMADSTATE_MAX;
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
             auto plane = [&](int k, int b) -> uint32_t { return (HALF && k == FW) ? PS[b] : P[c][k < FW ? k : 0][b]; };
@@ -293,32 +323,40 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
                 alive[k] = k == NWC - 1 ? (HALF ? last_mask << (4 * c) : last_mask) : 0xFFFFFFFFu;
                 if (EVEN) alive2[k] = alive[k];
             }
-            // State of the select: rc = rank - (number of alive rows), always negative, where rank is the 0-based
-            // rank of the lower middle among the alive rows.  With `ones` alive rows having the bit set,
-            // d = rc + ones = rank - zeros decides the bit (0 iff d < 0), and the new rc is d for bit 0 (the zeros
-            // stay alive) and unchanged for bit 1 (rank and the alive count both drop by zeros): rank itself
-            // never has to be kept.  lo_acc / hi_acc collect  sum_b m_b 2^b  with m_b = -1 where the bit is 0 (IMAD,
-            // FMA pipe: the LOP3 pipe is the one this kernel fills), so the value is 255 + acc.
-            int rc = ((T - 1) >> 1) - T;
-            const int ONE = (int)one, NEG1 = -(int)one, TWO = (int)one << 1;
+            int rc = ((T - 1) >> 1) - T, rc2 = (T >> 1) - T;
             int lo_acc = 0, hi_acc = 0;
-            int diverged = 0;                            // all-ones once the two middles sit in different sets
+            int diverged = 0;                            // shared count: all-ones once the two middles sit in different sets
 #pragma unroll
             for (int b = 7; b >= 0; --b) {
-                int d = rc;
+                int d, m0;
+                if constexpr (kImadState) {
+                    int nones = 0;                       // minus the number of alive rows with the bit set
 #pragma unroll
-                for (int k = 0; k < NWC; ++k) d = popc_acc(alive[k] & plane(k, b), d, one);
-                uint32_t any0 = 0u;                      // rows of the upper middle's set whose bit is 0
-                if (EVEN) {
+                    for (int k = 0; k < NWC; ++k) nones = imad(__popc(alive[k] & plane(k, b)), NEG1, nones);
+                    d = imad(nones, NEG1, rc);
+                    m0 = d >> 31;                        // all-ones: the bit is 0
+                    rc = imad(nones, m0, rc);
+                } else {
+                    d = rc;
+#pragma unroll
+                    for (int k = 0; k < NWC; ++k) d = popc_acc(alive[k] & plane(k, b), d, one);
+                    m0 = d >> 31;
+                    rc = isel(d, rc, m0);
+                }
+                lo_acc = imad(lo_acc, TWO, m0);
+                if constexpr (kTwoSelects) {
+                    int nones2 = 0;
+#pragma unroll
+                    for (int k = 0; k < NWC; ++k) nones2 = imad(__popc(alive2[k] & plane(k, b)), NEG1, nones2);
+                    const int m2 = imad(nones2, NEG1, rc2) >> 31;
+                    rc2 = imad(nones2, m2, rc2);
+                    hi_acc = imad(hi_acc, TWO, m2);
+#pragma unroll
+                    for (int k = 0; k < NWC; ++k) alive2[k] &= plane(k, b) ^ (uint32_t)m2;
+                } else if constexpr (EVEN) {
+                    uint32_t any0 = 0u;                  // rows of the upper middle's set whose bit is 0
 #pragma unroll
                     for (int k = 0; k < NWC; ++k) any0 |= alive2[k] & ~plane(k, b);
-                }
-                const int m0 = d >> 31;                  // all-ones: the bit is 0
-                rc = isel(d, rc, m0);
-                lo_acc = imad(lo_acc, TWO, m0);
-#pragma unroll
-                for (int k = 0; k < NWC; ++k) alive[k] &= plane(k, b) ^ (uint32_t)m0;
-                if (EVEN) {
                     // shared state: the upper middle has rank + 1, its bit is 0 iff d + 1 < 0; own state: iff any0
                     const int m0_shared = imad(ONE, ONE, d) >> 31;
                     const int m0_own = imad(__popc(any0), NEG1, 0) >> 31;
@@ -328,6 +366,8 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
 #pragma unroll
                     for (int k = 0; k < NWC; ++k) alive2[k] &= plane(k, b) ^ (uint32_t)m2;
                 }
+#pragma unroll
+                for (int k = 0; k < NWC; ++k) alive[k] &= plane(k, b) ^ (uint32_t)m0;
             }
             const int lo = 255 + lo_acc, hi = 255 + hi_acc;
             med[c] = EVEN ? ((lo + hi) >> 1) : lo;

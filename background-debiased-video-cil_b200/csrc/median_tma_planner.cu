@@ -29,6 +29,8 @@ struct Tuning {
     int ldsm_strips = 0;   // 128-byte strips per CTA tile of the transposing-load kernel; 0 = by parity (see below)
     int ldsm_stages = 0;   // tile buffers per CTA; 0 = as many (up to 4) as fit beside the target CTA count
     int ldsm_blocks = 0;   // CTAs per SM; 0 = register limit (8 / strips for T <= 192, 6 / strips above)
+    int l2_policy = -1;    // -1 = evict_normal (see median_ldsm.cuh), else 0 / 1 / 2
+    int l2_promo = -1;     // -1 = 256 B for aligned rows, 128 B otherwise; else 0, 64, 128, 256
 };
 
 Tuning read_tuning()
@@ -39,6 +41,8 @@ Tuning read_tuning()
     if (const char *s = getenv("BGD_LDSM_STRIPS")) { const int v = atoi(s); t.ldsm_strips = v >= 2 ? 2 : (v == 1 ? 1 : 0); }
     if (const char *s = getenv("BGD_LDSM_STAGES")) t.ldsm_stages = std::max(0, std::min(8, atoi(s)));
     if (const char *s = getenv("BGD_LDSM_BLOCKS")) t.ldsm_blocks = std::max(0, atoi(s));
+    if (const char *s = getenv("BGD_TMA_POLICY")) t.l2_policy = std::max(-1, std::min(2, atoi(s)));
+    if (const char *s = getenv("BGD_TMA_L2PROMO")) t.l2_promo = atoi(s);
     if (const char *s = getenv("BGD_COL_THREADS_C2")) t.threads_c2 = atoi(s) >= 256 ? 256 : 128;
     if (const char *s = getenv("BGD_COL_THREADS_C4")) { const int v = atoi(s); t.threads_c4 = v >= 256 ? 256 : (v >= 192 ? 192 : (v >= 128 ? 128 : 64)); }
     return t;
@@ -64,6 +68,23 @@ bool classify(int T, const Tuning &tn, bool use_ldsm, Key *k)
         }
     }
     return false;
+}
+
+// Alive mask of the last plane word of a column in the transposing-load kernel (median_ldsm.cuh): NH half groups of 16
+// rows, NWC = ceil(NH / 2) words; bit 8 y + m of a word is row 32 (NWC - 1) + 4 m + y of the column; when NH is odd the
+// last word is shared by the lane's two columns, 16 rows (m < 4) each, and the kernel shifts the mask by 4 for the second.
+uint32_t ldsm_last_mask(int T, int NH)
+{
+    const bool half = (NH & 1) != 0;
+    const int nwc = NH / 2 + (half ? 1 : 0);
+    const int n = T - 32 * (nwc - 1), cap = half ? 4 : 8;
+    uint32_t mask = 0u;
+    for (int y = 0; y < 4; ++y) {
+        int cnt = (n - y + 3) >> 2;
+        cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
+        mask |= ((1u << cnt) - 1u) << (8 * y);
+    }
+    return mask;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -136,27 +157,40 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
                 if (r != CUDA_SUCCESS)
                     return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a box of %d rows", (int)r, 1 << k);
             }
-            if (any_ldsm) {
-                const cuuint32_t box[2] = {(cuuint32_t)ldsm::kStripW, (cuuint32_t)1 << k};
-                const CUresult r = encode(&lprm.maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
-                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS)
-                    return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a swizzled box of %d rows", (int)r, 1 << k);
-            }
         }
     }
+    // swizzled maps of the transposing-load kernel: built per launch below (the box height depends on the class)
+    const cuuint64_t l_gdim[2] = {(cuuint64_t)N, (cuuint64_t)(row_hi - row_lo)};
+    const cuuint64_t l_gstride[1] = {(cuuint64_t)N};
+    const cuuint32_t l_estride[2] = {1, 1};
+    void *l_base = const_cast<uint8_t *>(d_frames) + row_lo * N;
+    const bool rows_aligned = N % 128 == 0 && reinterpret_cast<uintptr_t>(l_base) % 128 == 0;
+    const int promo_bytes = tn.l2_promo >= 0 ? tn.l2_promo : (rows_aligned ? 256 : 128);
+    const CUtensorMapL2promotion promo = promo_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                         : (promo_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                            : (promo_bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
+    auto ldsm_map = [&](CUtensorMap *out, int box_rows) -> int {
+        const cuuint32_t box[2] = {(cuuint32_t)ldsm::kStripW, (cuuint32_t)box_rows};
+        const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, l_base, l_gdim, l_gstride, box, l_estride,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(BGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a swizzled box of %d rows", (int)r, box_rows);
+        return BGD_OK;
+    };
+    (void)any_ldsm;
 
     // one table upload for all classes: row0[V] | out[V] | T[V], in class order
     Workspace &ws = thread_workspace();
-    const size_t tbl_bytes = (size_t)n_vid * (8 + 8 + 4);
+    const size_t tbl_bytes = (size_t)n_vid * (8 + 8 + 4 + 4);
     if (int rc = ws.acquire(tbl_bytes)) return rc;
     int64_t *h_row0 = static_cast<int64_t *>(ws.h_pinned);
     int64_t *h_out = h_row0 + n_vid;
     int32_t *h_T = reinterpret_cast<int32_t *>(h_out + n_vid);
+    uint32_t *h_mask = reinterpret_cast<uint32_t *>(h_T + n_vid);
     const int64_t *d_row0 = static_cast<const int64_t *>(ws.d_ptr);
     const int64_t *d_outi = d_row0 + n_vid;
     const int32_t *d_T = reinterpret_cast<const int32_t *>(d_outi + n_vid);
+    const uint32_t *d_mask = reinterpret_cast<const uint32_t *>(d_T + n_vid);
     {
         int64_t pos = 0;
         for (auto &kv : classes)
@@ -164,6 +198,7 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
                 h_row0[pos] = h_offsets[v] - row_lo;
                 h_out[pos] = v;
                 h_T[pos] = (int32_t)(h_offsets[v + 1] - h_offsets[v]);
+                h_mask[pos] = kv.first.C == 0 ? ldsm_last_mask(h_T[pos], kv.first.NW) : 0u;
                 ++pos;
             }
     }
@@ -179,6 +214,7 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
             lprm.vid_row0 = d_row0 + pos;
             lprm.vid_T = d_T + pos;
             lprm.vid_out = d_outi + pos;
+            lprm.vid_mask = d_mask + pos;
             lprm.N = N;
             // odd videos of more than 160 frames run close to the HBM limit and gain from wider rows per copy (+8 % at T = 181);
             // even T (bound by the LOP3 pipe) and short videos gain from the finer-grained CTAs (+3..6 %)
@@ -194,6 +230,18 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
             }
             lprm.rows_cap = key.NW * 16;
             lprm.one = 1u;
+            lprm.l2_policy = tn.l2_policy >= 0 ? tn.l2_policy : 1;
+            if (key.NW <= ldsm::kMaxNH) {
+                // one box of exactly T rows per frame count present in this class: T = 16 (NW - 1) + 1 (+ 1) + 2 j
+                const int t_lo = 16 * (key.NW - 1) + 1 + (key.even ? 1 : 0);
+                bool present[8] = {false, false, false, false, false, false, false, false};
+                for (int64_t i = 0; i < nv; ++i) present[(h_T[pos + i] - t_lo) >> 1] = true;
+                for (int j = 0; j < 8 && rc == BGD_OK; ++j)
+                    if (present[j]) rc = ldsm_map(&lprm.maps[j], t_lo + 2 * j);
+            } else {
+                for (int k = 0; k < kNumMaps && rc == BGD_OK; ++k) rc = ldsm_map(&lprm.maps[k], 1 << k);
+            }
+            if (rc) break;
             // buffers + mbarriers + slack to align the buffers to the 1024-byte swizzle atom; as many stages as
             // fit beside the CTA count the registers allow (1 KB per CTA is reserved by the driver)
             const size_t tile_bytes = (size_t)lprm.rows_cap * tile_w;
