@@ -255,6 +255,16 @@ class BackgroundMixDataset(_Base):
             self._pool_key = key
         return self._pool
 
+    def attach_pool(self, paths: Sequence[str], ragged: RaggedPool) -> None:
+        """Use backgrounds that are already on the device -- the result of ``pool.gather_extracted_backgrounds`` after a
+        sharded extraction -- instead of decoding ``bg_files`` again: ``paths[i]`` is image ``i`` of ``ragged``.  Paths
+        are matched after ``realpath`` like ``bg_dir`` (comix_loader.py:61-68); files of ``bg_files`` that are not among
+        them are decoded on demand as usual."""
+        store = BackgroundStore(self.bg_resize, ragged.device)
+        store.adopt([osp.realpath(p) for p in paths], ragged)
+        self._store, self._pool, self._pool_key = store, None, None
+        self.device = ragged.device
+
     # ---- per-sample API (reference contract) ---------------------------------------------------
     def prepare_train_frames(self, idx):
         """Prepare the frames for training given the index (comix_loader.py:105-124)."""

@@ -54,6 +54,11 @@ def parse_args(argv=None):
     # extensions
     parser.add_argument('--decode_threads', type=int, default=0, help='host decoder threads per shard; 0 = the host cores divided by the shards')
     parser.add_argument('--slab_mb', type=int, default=512)
+    parser.add_argument('--gather_pool', action='store_true',
+                        help='under torchrun: after the extraction, all-gather the decoded backgrounds into a mix pool '
+                             'resident on every GPU (main() returns (paths, RaggedPool))')
+    parser.add_argument('--gather_pool_resize', action='store_true',
+                        help='with --gather_pool: set the pool up for Resize(--size) inside the blend (the reference\'s bg_resize)')
     return parser.parse_args(argv)
 
 
@@ -291,6 +296,9 @@ def main(argv=None):
     else:
         raise ValueError
 
+    if _under_torchrun():
+        return _main_torchrun(args, output_dir, video_paths, len(extracted), avg_method)
+
     splits = _shard.contiguous_splits(video_paths, args.num_workers)
     if args.decode_threads <= 0:
         args.decode_threads = max(1, min(32, len(os.sched_getaffinity(0)) // max(1, sum(1 for s_ in splits if len(s_)))))
@@ -303,6 +311,53 @@ def main(argv=None):
     print(json.dumps({"extracted": len(video_paths), "skipped_existing": len(extracted), "backgrounds_indexed": len(index),
                       "seconds": round(seconds, 3), "videos_per_s": round(len(video_paths) / seconds, 2) if seconds > 0 else None,
                       "shards": sum(1 for s_ in splits if len(s_)), "method": args.method}))
+
+
+def _under_torchrun() -> bool:
+    return int(os.environ.get("WORLD_SIZE", "1")) >= 1 and "RANK" in os.environ and "MASTER_ADDR" in os.environ
+
+
+def _main_torchrun(args, output_dir, video_paths, n_skipped, avg_method):
+    """``torchrun --nproc-per-node N -m bgdebias_b200.extract_background ...``: one rank = one process = one GPU = one
+    contiguous slice of the sorted video list (the reference's split, extract_background.py:128-133, over ranks
+    instead of forked workers); no collective on the extraction itself.  With ``--gather_pool`` the ranks then run the
+    path's one collective (``pool.gather_extracted_backgrounds``) and return the device-resident mix pool."""
+    import torch.distributed as dist
+    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    device = local_rank % max(1, torch.cuda.device_count())
+    torch.cuda.set_device(device)
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    mine = _shard.contiguous_splits(video_paths, world)[rank]
+    if args.decode_threads <= 0:
+        args.decode_threads = max(1, min(32, len(os.sched_getaffinity(0)) // world))
+    method = bg_extraction_tmf if args.method == 'tmf' else sim_cam_motion_bg_extract
+    t0 = time.perf_counter()
+    failures = bg_extract_multiple(mine, output_dir, args.from_video, args.interval, args.max_frames, rank, method, avg_method,
+                                   device, args.decode_threads, args.slab_mb)
+    counts = [None] * world
+    dist.all_gather_object(counts, (len(mine), [f[0] for f in failures]))     # also the barrier: every JPEG is on disk
+    seconds = time.perf_counter() - t0
+    if rank == 0:
+        index = write_background_index(output_dir, args.image_suffix)
+        print(json.dumps({"extracted": len(video_paths), "skipped_existing": n_skipped, "backgrounds_indexed": len(index),
+                          "seconds": round(seconds, 3), "videos_per_s": round(len(video_paths) / seconds, 2) if seconds > 0 else None,
+                          "shards": world, "launcher": "torchrun", "method": args.method}))
+    failed = [f for _, fs in counts for f in fs]
+    pool = None
+    if not failed and args.gather_pool:
+        from .pool import gather_extracted_backgrounds
+        dist.barrier()                                                          # the index / directory listing is complete
+        pool = gather_extracted_backgrounds(output_dir, args.image_suffix, args.size if args.gather_pool_resize else None,
+                                            torch.device("cuda", device))
+    if own_group:
+        dist.barrier()
+        dist.destroy_process_group()
+    if failed:
+        raise RuntimeError(f"{len(failed)} videos failed: {failed[:5]}")
+    return pool
 
 
 INDEX_SUFFIX = ".bg_index.json"

@@ -287,11 +287,16 @@ class BackgroundPool:
 
     # ---- one collective: assemble the pool from per-rank shards ----------
     @staticmethod
-    def all_gather(local_names: Sequence[str], local_bgs: torch.Tensor, group=None):
+    def all_gather(local_names: Sequence[str], local_bgs: torch.Tensor, group=None, events=None):
         """All-gather per-rank backgrounds ``[P_r, ...]`` (uint8 or fp32, any device the backend
         supports) and their names.  Returns ``(names, tensor)`` in rank order, identical on every
         rank -- the index the single-process run would have produced for the rank-ordered list.
-        Shards may differ in size: counts are exchanged first, pixels travel padded to the max."""
+
+        The pixels are gathered IN PLACE: every rank's shard lands at its final position of the result, no padded
+        staging copy and no concatenation.  Shards of equal size (and the contiguous ceil split of
+        extract_background.py:128-133, where only the last shard is shorter) need nothing else; for any other
+        mix of sizes one compacting copy follows.  ``events``: optional pair of CUDA events recorded around the pixel
+        collective alone (the name exchange before it is host work)."""
         import torch.distributed as dist
         world = dist.get_world_size(group)
         names_per_rank: List[Optional[list]] = [None] * world
@@ -301,14 +306,74 @@ class BackgroundPool:
             raise ValueError("one name per local background")
         max_n = max(counts) if counts else 0
         item_shape = tuple(local_bgs.shape[1:])
-        padded = local_bgs.new_zeros((max_n,) + item_shape)
-        padded[: local_bgs.shape[0]] = local_bgs
-        gathered = local_bgs.new_empty((world * max_n,) + item_shape)
-        dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
-        gathered = gathered.view((world, max_n) + item_shape)
-        parts = [gathered[r, : counts[r]] for r in range(world)]
         names = [n for per in names_per_rank for n in per]
-        return names, torch.cat(parts, 0) if parts else gathered.view((0,) + item_shape)
+        if max_n == 0:
+            return names, local_bgs.new_empty((0,) + item_shape)
+        send = local_bgs.contiguous()
+        if send.shape[0] < max_n:                          # a short shard sends a padded copy (only its own, small, side)
+            send = torch.cat([send, send.new_zeros((max_n - send.shape[0],) + item_shape)])
+        gathered = local_bgs.new_empty((world * max_n,) + item_shape)
+        if events is not None:
+            events[0].record()
+        dist.all_gather_into_tensor(gathered, send, group=group)
+        if events is not None:
+            events[1].record()
+        total = sum(counts)
+        if all(c == max_n for c in counts[:-1]):           # gaps only after the last shard: the result is a prefix view
+            return names, gathered[:total]
+        # any other mix of shard sizes (not produced by the extraction's split): one compacting copy
+        return names, torch.cat([gathered[r * max_n:r * max_n + c] for r, c in enumerate(counts)], 0)
+
+
+def all_gather_ragged(local_names: Sequence[str], local: "RaggedPool", group=None):
+    """The same collective for backgrounds of mixed sizes: every rank contributes the byte buffer of its
+    :class:`RaggedPool` (the decoded JPEGs it extracted) and the image sizes; the gathered ``[world, max_bytes]``
+    buffer IS the pool of the result -- the slot table carries each image's offset, so nothing is moved or padded
+    after the collective.  Returns ``(names, RaggedPool)`` in rank order, identical on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    meta = [(str(n), int(s["offset"]), int(s["h"]), int(s["w"])) for n, s in zip(local_names, local.slots)]
+    if len(meta) != len(local):
+        raise ValueError("one name per local background")
+    metas: List[Optional[list]] = [None] * world
+    dist.all_gather_object(metas, (int(local.used), meta), group=group)
+    max_bytes = (max(u for u, _ in metas) + 15) & ~15
+    out = RaggedPool(local.bg_resize, local.device)
+    if max_bytes == 0:
+        return [], out
+    send = torch.zeros(max_bytes, dtype=torch.uint8, device=local.device)
+    if local.used:
+        send[:local.used].copy_(local.data[:local.used])
+    out.data = torch.empty(world * max_bytes, dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(out.data, send, group=group)
+    out.used = world * max_bytes
+    names, slots = [], []
+    for r, (_, per) in enumerate(metas):
+        for n, off, h, w in per:
+            names.append(n)
+            slots.append(out.make_slot(r * max_bytes + off, h, w))
+    out.slots = np.array(slots, dtype=SLOT_DTYPE) if slots else np.zeros(0, dtype=SLOT_DTYPE)
+    return names, out
+
+
+def gather_extracted_backgrounds(output_dir, image_suffix: str = ".jpg", bg_resize: Optional[int] = 256, device="cuda",
+                                 group=None):
+    """After a sharded extraction (``extract_background`` under torchrun: one rank = one GPU = one contiguous slice of
+    the sorted video list, extract_background.py:128-133) every rank holds the JPEGs it wrote.  This is the path's one
+    collective: each rank decodes ITS files with ``torchvision.io.read_image(mode=RGB)`` -- the JPEG round trip is part
+    of what the reference mixes (libs/loader/comix_loader.py:130), so the raw medians are not gathered -- and the
+    pixels + names are all-gathered over NCCL / NVLink into a pool resident on every GPU.  Returns
+    ``(paths, RaggedPool)``: the same index and pixels as decoding the whole directory on one rank."""
+    import pathlib
+    import torch.distributed as dist
+    from torchvision.io import ImageReadMode, read_image
+    from .shard import contiguous_splits
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    files = sorted(str(f) for f in pathlib.Path(output_dir).glob("*" + image_suffix))
+    mine = contiguous_splits(files, world)[rank] if files else []
+    local = RaggedPool(bg_resize, device)
+    local.append(_map_in_order(lambda f: read_image(f, mode=ImageReadMode.RGB), mine))
+    return all_gather_ragged(mine, local, group)
 
 
 class BackgroundStore:
@@ -372,6 +437,19 @@ class BackgroundStore:
         for i, n in enumerate(new):
             self.slot_of[n] = used + i
         self.decoded += len(new)
+
+    def adopt(self, names: Sequence[str], ragged: "RaggedPool") -> None:
+        """Start from an already resident pool (``gather_extracted_backgrounds``): ``names[i]`` is image ``i`` of
+        ``ragged``; nothing is decoded.  Only for an empty store."""
+        if len(self.slot_of):
+            raise ValueError("adopt() needs an empty store")
+        if len(names) != len(ragged) or ragged.bg_resize != self.bg_resize:
+            raise ValueError("one name per image, same bg_resize")
+        self.ragged = ragged
+        self.device = ragged.device
+        self.slot_of = {}
+        for i, n in enumerate(names):
+            self.slot_of.setdefault(n, i)                # a repeated name keeps its first image
 
     def _budget(self) -> int:
         if self.dense_budget_bytes is not None:

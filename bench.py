@@ -425,16 +425,41 @@ def run_ours(args):
             del all_bgs
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            all_names, all_bgs = BackgroundPool.all_gather(names, out)
-            g1.record()
+            t_host = time.perf_counter()
+            all_names, all_bgs = BackgroundPool.all_gather(names, out, events=(g0, g1))
             barrier()
+            t_host = time.perf_counter() - t_host
             tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
             dist.all_reduce(tg, op=dist.ReduceOp.MAX)
             same = bool(torch.equal(all_bgs[rank * V:(rank + 1) * V], out)) and len(all_names) == world * V
             gather = {"ms": float(tg.item()), "backgrounds": int(all_bgs.shape[0]), "bytes_per_rank_out": int(all_bgs.numel()),
-                      "GB/s_per_rank": all_bgs.numel() / (float(tg.item()) * 1e-3) / 1e9, "backend": "nccl", "parity": same}
+                      "GB/s_per_rank": all_bgs.numel() / (float(tg.item()) * 1e-3) / 1e9, "backend": "nccl", "parity": same,
+                      "in_place": True, "ms_with_name_exchange_host_clock": t_host * 1e3}
             del all_bgs
+            # the product flow at small scale: every rank writes 16 of its backgrounds as JPEGs (what the CLI does),
+            # the ranks gather the decoded files (pool.gather_extracted_backgrounds) and rank 0 compares the gathered
+            # pool with its own decode of the whole directory (what BackgroundPool.from_files reads)
+            import cv2, tempfile, shutil
+            from torchvision.io import ImageReadMode, read_image
+            from bgdebias_b200.pool import gather_extracted_backgrounds
+            holder = [tempfile.mkdtemp(prefix="bgd_bench_pool_") if rank == 0 else None]
+            dist.broadcast_object_list(holder, src=0)
+            small = out[:16].cpu().numpy().reshape(16, H, W, 3)
+            for i in range(16):
+                cv2.imwrite(os.path.join(holder[0], f"r{rank}_v{i:03d}.jpg"), small[i])
+            barrier()
+            paths, rp = gather_extracted_backgrounds(holder[0], ".jpg", 256, dev)
+            flow_ok = len(paths) == 16 * world
+            if rank == 0:
+                for k in range(0, len(paths), max(1, len(paths) // 8)):
+                    s_ = rp.slots[k]
+                    ref = read_image(paths[k], mode=ImageReadMode.RGB).to(dev)
+                    o_ = int(s_["offset"])
+                    flow_ok = flow_ok and bool(torch.equal(rp.data[o_:o_ + ref.numel()].view_as(ref), ref))
+            barrier()
+            if rank == 0:
+                shutil.rmtree(holder[0], ignore_errors=True)
+            gather["product_flow"] = {"files": len(paths), "equals_decoding_the_directory": flow_ok}
         except Exception as e:
             gather = {"error": repr(e)}
 

@@ -115,3 +115,59 @@ def test_many_threads_small_slabs_mixed_sizes(tmp_path):
              "--decode_threads", "8", "--slab_mb", "1"])
     for name, fr in videos.items():
         assert (odir / f"{name}.jpg").read_bytes() == _expected_jpeg(list(fr), 1, 500, tmp_path), name
+
+
+def test_sharded_extraction_then_gathered_pool_feeds_the_mix(tmp_path, monkeypatch):
+    """The product flow of the path's one collective, as `torchrun -m bgdebias_b200.extract_background --gather_pool`
+    runs it (here: world size 1 over NCCL in-process): extraction writes the JPEGs (byte-identical to the reference's),
+    the ranks all-gather the JPEG-round-tripped pixels into a resident pool, and a BackgroundMixDataset fed with that
+    pool blends exactly like one that decodes the directory itself (comix_loader.py:84-103,126-131)."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from bgdebias_b200 import comix_loader as cl, extract_background as eb
+    from oracle import bgmix_oracle as bo
+    rng = np.random.default_rng(11)
+    vdir, odir = tmp_path / "videos", tmp_path / "bg"
+    vdir.mkdir()
+    names = ["p", "q", "r", "s"]
+    for name, T in zip(names, [5, 12, 8, 3]):
+        base = rng.integers(0, 256, (1, H, W, 3), dtype=np.uint8)
+        _write(vdir / f"{name}.avi", np.clip(base.astype(np.int16) + rng.integers(-30, 31, (T, H, W, 3)), 0, 255).astype(np.uint8))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    for k, v in dict(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port)).items():
+        monkeypatch.setenv(k, v)
+    assert not dist.is_initialized()
+    paths, ragged = eb.main(["--video_dir", str(vdir), "--output_dir", str(odir), "--from_video", "--gather_pool",
+                             "--gather_pool_resize", "--size", "56"])
+    assert not dist.is_initialized()
+    assert [pathlib.Path(p).name for p in paths] == [f"{n}.jpg" for n in names] and len(ragged) == 4
+
+    T, crop, B = 2, (40, 40), 6
+    fg = rng.integers(0, 256, (B, T, 40, 40, 3), dtype=np.uint8)
+    infos = [dict(frame_dir=f"/x/{names[i % 4]}", total_frames=T, label=i, sample=i) for i in range(B)]
+    pipeline = lambda info: dict(imgs=torch.from_numpy(fg[info["sample"]]), label=torch.tensor([0]), randAug=False)
+    outs = []
+    for attach in (True, False):
+        calls = []
+        from torchvision.io import ImageReadMode, read_image
+        ds = cl.BackgroundMixDataset(infos, pipeline, bg_dir=str(odir), bg_resize=56, bg_crop_size=crop, with_randAug=True,
+                                     device_mix=True, bg_reader=lambda p: (calls.append(p), read_image(p, mode=ImageReadMode.RGB))[1])
+        if attach:
+            ds.attach_pool(paths, ragged)
+        torch.manual_seed(3)
+        samples = [ds.prepare_train_frames(i) for i in range(B)]
+        outs.append(ds.gpu_collate(samples)["imgs"].cpu().numpy())
+        assert (len(calls) == 0) == attach                      # the gathered pool is used as is: nothing is decoded again
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    # and against the oracle on the decoded JPEGs
+    from oracle import aa_resize_oracle as ao
+    torch.manual_seed(3)
+    exp = []
+    for i in range(B):
+        b, t, l = bo.draw_bg_params(len(ds.bg_files), *ao.resized_hw(H, W, 56), crop)
+        img = read_image(str(odir / f"{pathlib.Path(ds.bg_files[b]).stem}.jpg"), mode=ImageReadMode.RGB).numpy()
+        exp.append(bo.mix_clip(fg[i], ao.aa_resize(img, 56), t, l, crop, 0.5, True))
+    assert np.array_equal(outs[0].view(np.uint32), np.stack(exp).view(np.uint32))

@@ -175,6 +175,55 @@ def test_pool_all_gather_two_ranks():
         assert [int(bgs[i, 0, 0, 0]) for i in range(4)] == [1, 2, 3, 2]
 
 
+def _gather_dir_worker(rank, world, port, bg_dir, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bgdebias_b200.pool import BackgroundPool, gather_extracted_backgrounds
+    paths, pool = gather_extracted_backgrounds(bg_dir, ".jpg", 40, "cpu")
+    imgs = []
+    for s in pool.slots:
+        o, h, w = int(s["offset"]), int(s["h"]), int(s["w"])
+        imgs.append(pool.data[o:o + 3 * h * w].view(3, h, w).numpy().copy())
+    # shards in an order the extraction's split never produces (first shard shorter): the compacting branch
+    n = 1 if rank == 0 else 3
+    names, bgs = BackgroundPool.all_gather([f"r{rank}_{i}" for i in range(n)], torch.full((n, 2, 2), 10 * rank, dtype=torch.uint8) + torch.arange(n, dtype=torch.uint8).view(n, 1, 1))
+    q.put((rank, paths, imgs, [(int(s["Hb"]), int(s["Wb"])) for s in pool.slots], names, bgs.numpy()))
+    dist.destroy_process_group()
+
+
+def test_gather_of_extracted_backgrounds_equals_decoding_the_directory(tmp_path):
+    """The path's one collective as the product runs it after a sharded extraction (world size 2, gloo, CPU): every rank
+    decodes the JPEGs of its own slice and the all-gathered pool holds, in sorted-name order, exactly the pixels
+    torchvision.io.read_image returns for every file of the directory -- what BackgroundPool.from_files decodes and what
+    the reference's _get_bg_image reads (comix_loader.py:130)."""
+    import multiprocessing as mp
+    import cv2
+    from torchvision.io import ImageReadMode, read_image
+    rng = np.random.default_rng(3)
+    sizes = [(36, 48), (36, 64), (40, 40), (36, 48), (50, 30)]
+    for i, (h, w) in enumerate(sizes):
+        cv2.imwrite(str(tmp_path / f"v{i:02d}.jpg"), rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_dir_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    files = sorted(str(f) for f in tmp_path.glob("*.jpg"))
+    from bgdebias_b200.pool import resized_hw
+    for rank, paths, imgs, hws, names, bgs in res:
+        assert paths == files
+        for f, im, hw in zip(files, imgs, hws):
+            ref = read_image(f, mode=ImageReadMode.RGB).numpy()
+            assert np.array_equal(im, ref) and hw == resized_hw(ref.shape[1], ref.shape[2], 40)
+        assert names == ["r0_0", "r1_0", "r1_1", "r1_2"] and [int(b[0, 0]) for b in bgs] == [0, 10, 11, 12]
+
+
 def test_background_store_slots_without_gpu():
     """BackgroundStore on the CPU device: names are decoded once, pools are slot tables over shared pixels."""
     import numpy as np
