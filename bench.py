@@ -413,6 +413,20 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * rows_e * k_e2e / float(te.item())
     e2e_ok = bool(torch.equal(h_out.to(dev), out[:Ve]))
+    # the ceiling of that path on this box: the same pinned bytes through plain cudaMemcpyAsync (torch's copy_), all ranks
+    # at once -- what the PCIe links and the host's memory system give N concurrent H2D streams, no kernel, no D2H
+    scratch = torch.empty((rows_e, N_BYTES), dtype=torch.uint8, device=dev)
+    scratch.copy_(h_frames, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        scratch.copy_(h_frames, non_blocking=True)
+    torch.cuda.synchronize()
+    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    h2d_ceiling_gbs = world * rows_e * N_BYTES * k_e2e / float(tc.item()) / 1e9
+    del scratch
 
     # ---- the path's one collective: all-gather of the background index + pixels for the mix pool
     #      (pool.BackgroundPool.all_gather).  Outside `value`; reported beside it.
@@ -660,7 +674,10 @@ def run_ours(args):
                        "l2": "resident inputs (tens of GB per GPU) exceed L2; no flush needed", "kernel": "median_ldsm for T<=512, median_colplane above (AUTO)", "content": args.content,
                        "parallelism": f"shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": rows_e * N_BYTES,
-                    "d2h_bytes_per_step": Ve * N_BYTES, "videos_per_step": Ve, "parity": e2e_ok},
+                    "d2h_bytes_per_step": Ve * N_BYTES, "videos_per_step": Ve, "parity": e2e_ok,
+                    "h2d_GBs": e2e_value * N_BYTES / 1e9,
+                    "h2d_ceiling_GBs": h2d_ceiling_gbs, "frac_of_h2d_ceiling": e2e_value * N_BYTES / 1e9 / h2d_ceiling_gbs,
+                    "ceiling": "the same pinned bytes by plain cudaMemcpyAsync on all ranks at once (no kernel, no D2H), measured in this run"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": "profiles ncu capture (dram bytes per algorithmic byte of one --set full capture) x this step's algorithmic bytes",

@@ -239,6 +239,33 @@ def test_one_call_mixes_every_kernel_family(bgd):
         np.testing.assert_array_equal(out[v], c_oracle.temporal_median(fr[offs[v]:offs[v + 1]]), err_msg=f"T={T}")
 
 
+def test_long_videos_inside_a_mixed_batch_take_the_generic_kernel_alone(bgd):
+    """AUTO classifies every video, not the batch: the rawframes variant has no frame cap (comix_loader.py:157-161), so a
+    call can hold videos beyond the TMA kernels' 544 frames.  Those alone take the generic kernel (one launch per run of
+    consecutive long videos); the others keep the fast path."""
+    ops, cabi = bgd
+    cabi.set_median_variant(0)
+    rng = np.random.default_rng(12)
+    N = 1024 + 32
+    Ts = [530, 600, 1200, 64, 181, 700, 545, 544, 2]
+    offs = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+    fr = rng.integers(0, 256, (int(offs[-1]), N), dtype=np.uint8)
+    d_fr = torch.from_numpy(fr).cuda()
+    n0 = cabi.kernel_launch_count()
+    out = torch.ops.bgdebias.temporal_median_varlen(d_fr, torch.from_numpy(offs)).cpu().numpy()
+    launches = cabi.kernel_launch_count() - n0
+    for v, T in enumerate(Ts):
+        np.testing.assert_array_equal(out[v], c_oracle.temporal_median(fr[offs[v]:offs[v + 1]]), err_msg=f"T={T}")
+    # fast classes: 530 + 544 (column-plane), 64, 181, 2 -> at most 5 launches; generic: runs {600, 1200} and {700, 545} -> 2
+    assert 3 <= launches <= 7, launches
+    # a batch of long videos only still works (everything generic)
+    Ts2 = [600, 900]
+    offs2 = np.concatenate([[0], np.cumsum(Ts2)]).astype(np.int64)
+    out2 = torch.ops.bgdebias.temporal_median_varlen(d_fr[:1500], torch.from_numpy(offs2)).cpu().numpy()
+    for v in range(2):
+        np.testing.assert_array_equal(out2[v], c_oracle.temporal_median(fr[offs2[v]:offs2[v + 1]]))
+
+
 def test_concurrent_host_threads_and_streams(bgd):
     """Four host threads, each on its own CUDA stream, call the op concurrently (ctypes releases the GIL during
     the C-ABI call): per-thread workspaces and stream-ordered launches must not interfere."""
@@ -276,3 +303,29 @@ def test_concurrent_host_threads_and_streams(bgd):
         exp = np.stack([c_oracle.temporal_median(fr[offs[v]:offs[v + 1]]) for v in range(len(offs) - 1)])
         for o in results[i]:
             np.testing.assert_array_equal(o, exp)
+
+
+def test_calls_do_not_block_the_host(bgd):
+    """Stream-ordered means the host never waits for earlier kernels: eight varlen calls are enqueued behind a kernel that
+    keeps the stream busy for ~0.2 s, and the host is back before that kernel has finished (the per-thread table workspace is
+    a ring, so a call only ever waits for the call 16 calls before it)."""
+    import time
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(3)
+    Ts = rng.integers(20, 200, 24)
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64))
+    fr = torch.randint(0, 256, (int(offs[-1]), 4096), dtype=torch.uint8, device=dev)
+    ref = torch.ops.bgdebias.temporal_median_varlen(fr, offs)
+    torch.cuda.synchronize()
+    gate = torch.cuda.Event()
+    torch.cuda._sleep(int(0.2 * 1.9e9))                  # ~0.2 s of device time in front of the calls
+    gate.record()
+    t0 = time.perf_counter()
+    outs = [torch.ops.bgdebias.temporal_median_varlen(fr, offs) for _ in range(8)]
+    host_s = time.perf_counter() - t0
+    still_busy = not gate.query()
+    torch.cuda.synchronize()
+    assert still_busy, f"the host spent {host_s:.3f} s in 8 calls and the stream had drained: a call blocked"
+    assert host_s < 0.15
+    for o in outs:
+        assert torch.equal(o, ref)
