@@ -142,6 +142,21 @@ class RaggedPool:
         self.used = need
         self._slots_dev = None
 
+    @classmethod
+    def from_uniform_buffer(cls, data: torch.Tensor, n: int, h: int, w: int, bg_resize: Optional[int] = 256) -> "RaggedPool":
+        """``n`` images of one size already resident back to back in ``data`` (uint8, ``n * 3 * h * w`` bytes, planar
+        ``[3][h][w]`` each): adopt the buffer as a pool without copying -- e.g. the all-gathered backgrounds of a
+        dataset of one resolution kept as uint8 (Sth-Sth-v2: 220,847 x 240 x 427 x 3 = 67.9 GB)."""
+        if data.dtype != torch.uint8 or data.dim() != 1 or data.numel() < n * 3 * h * w:
+            raise ValueError("data must be a flat uint8 buffer of at least n * 3 * h * w bytes")
+        pool = cls(bg_resize, data.device)
+        pool.data, pool.used = data, n * 3 * h * w
+        one = pool.make_slot(0, h, w)
+        slots = np.repeat(np.array([one], dtype=SLOT_DTYPE), n)
+        slots["offset"] = np.arange(n, dtype=np.int64) * (3 * h * w)
+        pool.slots = slots
+        return pool
+
     @property
     def slots_tensor(self) -> torch.Tensor:
         """The slot table as a uint8 device tensor (``len(self) * 40`` bytes)."""
