@@ -178,6 +178,17 @@ class ClockSampler:
 
 
 
+def traffic_ratio(name):
+    """DRAM bytes per algorithmic byte of the kernel, from the committed `ncu --set full` capture (profiles/r2_traffic*.json)."""
+    try:
+        return float(json.loads((ROOT / "profiles" / name).read_text())["dram_bytes_per_algorithmic_byte"])
+    except Exception:
+        return None
+
+
+TRAFFIC_SOURCE = "profiles ncu capture: DRAM bytes per algorithmic byte of one `ncu --set full` launch of this kernel x this step's algorithmic bytes"
+
+
 def fill_frames(frames, Ts, offs, Hh, Ww, content, seed, torch):
     """Synthetic frames on the device.  "random": uniform bytes (the selection's worst case, every column has T distinct
     candidates).  "structured": what the temporal median is for -- one static background per video,
@@ -265,7 +276,10 @@ def extraction_leg(leg_name, spec, rank, world, dev, steps, barrier):
            "config": {"workload": wl["label"] + f"; resident chunk of {V} videos per GPU, content: {spec['content']}", "videos_per_gpu": V,
                       "frames_per_gpu": rows, "frame_shape": [Hh, Ww, 3], "T": wl["t_text"], "resident_gb": rows * n_bytes / 1e9},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_step": step_bytes, "traffic": None},
+                        "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_step": step_bytes,
+                        "traffic": (lambda r: r * step_bytes if r else None)(traffic_ratio(
+                            {"hmdb51": "r2_traffic_T180.json", "sthv2": "r2_traffic_sthv2_T48.json"}.get(leg_name, "r2_traffic.json"))),
+                        "traffic_source": TRAFFIC_SOURCE},
            "parity_spotcheck": ok}
     if leg_name == "sthv2" and world > 1:
         # Sth-Sth-v2's pool (67.9 GB of uint8 backgrounds) is not replicated: the ranks all-gather the INDEX
@@ -344,7 +358,9 @@ def ragged_mix_legs(rank, world, dev):
                 "config": {"workload": label, "pool_images": len(rp), "pool_resident_gb": rp.used / 1e9,
                            "l2": "256 MB flush write between iterations", "note": "output stays on the device (it is the training tensor)"},
                 "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / peak,
-                             "traffic": None, "algorithmic_bytes_per_step": by},
+                             "traffic": (lambda r: r * by if r else None)(traffic_ratio("r2_traffic_bgmix_ragged.json")),
+                             "traffic_source": TRAFFIC_SOURCE, "algorithmic_bytes_per_step": by,
+                             "note": "instruction-bound: the separable Resize of the background window runs inside the launch"},
                 "parity_spotcheck": ok}
 
     out = {}
@@ -641,7 +657,7 @@ def run_ours(args):
         peak, _ = measured_peak_gbs()
         mix_traffic = None
         try:
-            mix_traffic = json.loads((ROOT / "profiles" / "r1_traffic_bgmix.json").read_text())["dram_bytes_per_algorithmic_byte"] * mix_bytes
+            mix_traffic = json.loads((ROOT / "profiles" / "r2_traffic_bgmix.json").read_text())["dram_bytes_per_algorithmic_byte"] * mix_bytes
         except Exception:
             pass
         bgmix = {"metric": "bgmix_clips_per_sec", "value": world * B / (mix_ms * 1e-3), "unit": "clips/s",
@@ -704,7 +720,7 @@ def run_ours(args):
                             "sample": f"{4 * len(frames)} cv2.resize(frame, (224, 224), INTER_LINEAR) calls (the Resize step alone, 8 per clip), one thread"}
             tail_traffic = None
             try:
-                tail_traffic = json.loads((ROOT / "profiles" / "r1_traffic_resize_blend.json").read_text())["dram_bytes_per_algorithmic_byte"] * tail_bytes
+                tail_traffic = json.loads((ROOT / "profiles" / "r2_traffic_resize_blend.json").read_text())["dram_bytes_per_algorithmic_byte"] * tail_bytes
             except Exception:
                 pass
             bgmix["with_resize"] = {
@@ -759,7 +775,7 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         achieved = step_bytes / (ms_per_step * 1e-3) / 1e9          # this rank's step bytes / max step time
         traffic = None
-        tf = ROOT / "profiles" / "r1_traffic.json"
+        tf = ROOT / "profiles" / "r2_traffic.json"
         if tf.exists():
             try:
                 ratio = json.loads(tf.read_text())["dram_bytes_per_algorithmic_byte"]
