@@ -241,3 +241,83 @@ def test_sthv2_sized_uint8_pool_arithmetic_and_blend(env):
         resized[k] = ao.aa_resize(chunk[k].numpy(), 256)
     exp = np.stack([bo.mix_clip(fg[b], resized[int(idx[b]) % 64], int(top[b]), int(left[b]), (224, 224), 0.5, True) for b in range(B)])
     _assert_same(got, exp)
+
+
+class _U8Clips:
+    """Picklable stand-in for the mmaction pipeline up to (not including) Normalize."""
+    def __init__(self, fg, ra):
+        self.fg, self.ra = fg, ra
+
+    def __call__(self, info):
+        return dict(imgs=torch.from_numpy(self.fg[info["sample"]]), label=torch.tensor([info["label"]]), randAug=bool(self.ra[info["sample"]]))
+
+
+def test_real_jpeg_pool_of_two_sizes_behind_dataloader_workers(env, tmp_path):
+    """The whole M1-M3 chain on real files with the default reader: JPEGs of two sizes on disk (what the extraction CLI
+    writes for a dataset of mixed widths), DataLoader worker processes draw bg_idx and the crop from each image's own
+    resized size (header probe, no CUDA in the workers), the training process decodes every file once (read_image) and
+    blends per batch.  Expected = the oracle on torchvision's decode of the same files."""
+    import cv2
+    from torchvision.io import ImageReadMode, read_image
+    ops, cabi, cl, pool_mod = env
+    rng = np.random.default_rng(23)
+    T, H, W, n = 2, 32, 32, 12
+    names = [f"v{i:02d}" for i in range(6)]
+    for i, nm in enumerate(names):
+        h, w = (36, 48) if i % 2 == 0 else (40, 72)
+        base = cv2.resize(rng.integers(0, 256, (6, 8, 3), dtype=np.uint8), (w, h), interpolation=cv2.INTER_CUBIC)   # smooth: survives JPEG
+        cv2.imwrite(str(tmp_path / f"{nm}.jpg"), base)
+    fg = rng.integers(0, 256, (n, T, H, W, 3), dtype=np.uint8)
+    ra = rng.integers(0, 2, n).astype(bool)
+    infos = [dict(frame_dir=f"/x/{names[i % 6]}", total_frames=T, label=i, sample=i) for i in range(n)]
+    ds = cl.BackgroundMixDataset(infos, _U8Clips(fg, ra), bg_dir=str(tmp_path), bg_resize=40, bg_crop_size=(H, W), with_randAug=True,
+                                 device_mix=True)
+    assert len(ds.bg_files) == n
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=2, collate_fn=ds.host_collate, pin_memory=True)
+    decoded = {p: read_image(p, mode=ImageReadMode.RGB).numpy() for p in set(ds.bg_files)}
+    seen = 0
+    for batch in loader:
+        out = ds.device_finish(batch)["imgs"].cpu().numpy()
+        B = batch["imgs"].shape[0]
+        for b in range(B):
+            i = int(batch["bg_idx"][b])
+            assert (i == -1) == bool(ra[seen + b])
+            if i < 0:
+                exp = bo.fg_normalize(fg[seen + b], bo.fg_lut())
+            else:
+                img = decoded[ds.bg_files[i]]
+                Hb, Wb = ao.resized_hw(img.shape[1], img.shape[2], 40)
+                assert 0 <= int(batch["bg_top"][b]) <= Hb - H and 0 <= int(batch["bg_left"][b]) <= Wb - W
+                exp = bo.mix_clip(fg[seen + b], ao.aa_resize(img, 40), int(batch["bg_top"][b]), int(batch["bg_left"][b]), (H, W), 0.5, True)
+            _assert_same(out[b], exp)
+        seen += B
+    assert seen == n and ds.device_pool().tensor is None and len(ds._store) == 6
+
+
+def test_pool_without_resize_and_uniform_dense_choice(env):
+    """bg_resize=None (a pool already at crop scale): no table, no pass -- the ragged blend reads the bytes as they are; a
+    uniform store within budget serves the dense path, the same store with no budget the ragged path, same bits."""
+    ops, cabi, cl, pool_mod = env
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (3, 40, 56), dtype=np.uint8) for _ in range(4)]
+    B, T, H, W = 5, 2, 32, 32
+    fg = rng.integers(0, 256, (B, T, H, W, 3), dtype=np.uint8)
+    idx, top, left = [3, 0, 1, 2, 3], [0, 8, 3, 5, 1], [24, 0, 7, 9, 4]
+    exp = np.stack([bo.mix_clip(fg[b], imgs[idx[b]].astype(np.float32), top[b], left[b], (H, W), 0.5, True) for b in range(B)])
+    dev = torch.device("cuda")
+    t32 = lambda a: torch.tensor(a, dtype=torch.int32, device=dev)
+    lut, mean, std = ops.make_fg_lut(bo.DEFAULT_MEAN, bo.DEFAULT_STD, dev), torch.tensor(bo.DEFAULT_MEAN), torch.tensor(bo.DEFAULT_STD)
+    for budget in (None, 0):
+        store = pool_mod.BackgroundStore(None, dev, dense_budget_bytes=budget)
+        store.ensure([f"i{k}" for k in range(4)], lambda n: imgs[int(n[1:])])
+        dense = store.tensor
+        assert (dense is None) == (budget == 0)
+        app = torch.ones(B, dtype=torch.uint8, device=dev)
+        if dense is not None:
+            got = torch.ops.bgdebias.bgmix_blend(torch.from_numpy(fg).to(dev), dense, t32(idx), t32(top), t32(left), app, lut, mean, std, 0.5, "NTCHW")
+        else:
+            r = store.ragged
+            assert int(r.slots["xtab"][0]) == -1 and int(r.slots["ytab"][0]) == -1
+            got = torch.ops.bgdebias.bgmix_blend_ragged(torch.from_numpy(fg).to(dev), r.data, r.slots_tensor, r.tables.tensor, t32(idx), t32(top),
+                                                        t32(left), app, lut, mean, std, 0.5, "NTCHW")
+        _assert_same(got.cpu().numpy(), exp)
