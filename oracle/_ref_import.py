@@ -89,3 +89,37 @@ def load_actor_cut_mix_loader():
 def load_comix_loader():
     """The module at libs/loader/comix_loader.py (``BackgroundMixDataset`` :16-145)."""
     return _load("_ref_comix_loader", os.path.join("libs", "loader", "comix_loader.py"))
+
+
+def reference_median_of_frames():
+    """``frames -> median frame`` through the REFERENCE's own ``bg_extraction_tmf`` (cil_tools/extract_background.py:42-75)
+    with its file I/O stubbed out: ``cv2.VideoCapture`` is replaced by an in-memory capture that hands back the given
+    frames and ``cv2.imwrite`` by a no-op, so what runs (and what bench.py's CPU arm times in the build container) is the
+    reference's loop, its ``np.median(frames, axis=0).astype(np.uint8)`` and nothing of the codec."""
+    import types
+    ref = load_extract_background()
+
+    class _Capture:
+        def __init__(self, frames):
+            self.frames, self.i = frames, 0
+
+        def isOpened(self):
+            return True
+
+        def read(self):
+            if self.i >= len(self.frames):
+                return False, None
+            f = self.frames[self.i]
+            self.i += 1
+            return True, f
+
+    holder = {}
+    fake_cv2 = types.SimpleNamespace(**{k: getattr(ref.cv2, k) for k in dir(ref.cv2) if not k.startswith("__")})
+    fake_cv2.VideoCapture = lambda path: _Capture(holder["frames"])
+    fake_cv2.imwrite = lambda path, img: True
+    ref.cv2 = fake_cv2
+
+    def run(frames):
+        holder["frames"] = frames
+        return ref.bg_extraction_tmf("in-memory", "nowhere.jpg", True, 1, max(len(frames), 1))
+    return run
