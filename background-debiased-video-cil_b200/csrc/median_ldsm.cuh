@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     const int stages = prm.stages;
     const uint32_t stage_bytes = (uint32_t)prm.rows_cap * kTileW;
     uint64_t *bar = reinterpret_cast<uint64_t *>(buf + (size_t)stages * stage_bytes);   // bar[s]: buffer s is full
+    // desc[s] = {T, alive mask of the last word, columns of the tile inside the frame, -, output address of the tile}:
+    // written by the lane that requests tile s, read by every lane once the tile has landed -- the consumers keep no
+    // (video, column tile) cursor of their own and touch no table in global memory
+    uint4 *desc = reinterpret_cast<uint4 *>(bar + 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t one = prm.one;
 
@@ -205,6 +209,13 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         const int T = __shfl_sync(0xFFFFFFFFu, prm.vid_T[vid], 0);
         const int row0 = __shfl_sync(0xFFFFFFFFu, (int)prm.vid_row0[vid], 0);
         if (!elected) return;
+        {
+            const int64_t col0 = (int64_t)ct * kTileW;
+            const int64_t left = prm.N - col0;
+            const uint64_t dst = reinterpret_cast<uint64_t>(prm.out + prm.vid_out[vid] * prm.N + col0);
+            desc[2 * slot] = make_uint4((uint32_t)T, __ldg(prm.vid_mask + vid), (uint32_t)(left < kTileW ? left : kTileW), 0u);
+            desc[2 * slot + 1] = make_uint4((uint32_t)dst, (uint32_t)(dst >> 32), 0u, 0u);
+        }
         mbar_arrive_expect_tx(bar_s, (uint32_t)T * (uint32_t)kTileW);
         if constexpr (COLS == 2) {
             // the frame counts of a launch are 16 (NH - 1) + 1 (+ 1 for even T) + 2 j, j = 0..7: maps[j] has a box of
@@ -233,8 +244,8 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         }
     };
 
-    int tile = blockIdx.x, vid = tile / tpv, ct = tile - vid * tpv;
-    int ptile = tile, pvid = vid, pct = ct;              // the producer's cursor: `stages` tiles ahead
+    int tile = blockIdx.x;
+    int ptile = tile, pvid = tile / tpv, pct = tile - pvid * tpv;      // the producer's cursor: `stages` tiles ahead
     for (int s = 0; s < stages; ++s) {
         if (warp == (s & (kWarps - 1)) && ptile < num_tiles) issue_tile(pvid, pct, s);
         advance(ptile, pvid, pct);
@@ -243,12 +254,15 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     int slot = 0;
     int turn = stages;                                   // whose turn it is to request a tile (continues the prologue's rotation)
     uint32_t phases = 0;                                 // bit s: parity to wait for on bar[s]
-    for (; tile < num_tiles; advance(tile, vid, ct)) {
-        const int T = prm.vid_T[vid];
-        const uint32_t last_mask = __ldg(prm.vid_mask + vid);
-
+    for (; tile < num_tiles; tile += (int)gridDim.x) {
         mbar_wait(bar + slot, (phases >> slot) & 1u);
         phases ^= 1u << slot;
+        const uint4 d0 = desc[2 * slot];
+        const uint2 d1 = *reinterpret_cast<const uint2 *>(desc + 2 * slot + 1);
+        const int T = (int)d0.x;
+        const uint32_t last_mask = d0.y;
+        const int cols_valid = (int)d0.z;
+        uint8_t *dst = reinterpret_cast<uint8_t *>(((uint64_t)d1.y << 32) | d1.x);
         const uint32_t ld_slot = ld_base + (uint32_t)slot * stage_bytes;
 
         // ---- shared memory -> registers (transposing loads), then 8x8 bit transposes -----------
@@ -374,10 +388,8 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
         }
 
         // ---- store ---------------------------------------------------------------------------------------
-        const int64_t col0 = (int64_t)ct * kTileW;
-        uint8_t *dst = prm.out + prm.vid_out[vid] * prm.N + col0;
-        if (col0 + colA < prm.N) dst[colA] = (uint8_t)med[0];
-        if (COLS == 2 && col0 + colB < prm.N) dst[colB] = (uint8_t)med[1];
+        if (colA < cols_valid) dst[colA] = (uint8_t)med[0];
+        if (COLS == 2 && colB < cols_valid) dst[colB] = (uint8_t)med[1];
     }
 }
 

@@ -160,6 +160,12 @@ __device__ __forceinline__ int popc_acc32(uint32_t x, int acc, uint32_t one)    
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(__popc(x)), "r"(one), "r"(acc));
     return r;
 }
+__device__ __forceinline__ int imad32(int a, int b, int c)      // a * b + c issued as IMAD; the callers pass run-time operands
+{
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ int isel32(int a, int b, int mask)
 {
     int d;
@@ -227,39 +233,40 @@ __global__ void __launch_bounds__(kNanThreads) nan_median_planes_kernel(const fl
     if (nvalid == 0) {
         res = __uint_as_float(0x7FC00000u);
     } else {
-        // rc = rank - (number of alive rows), always negative; rank = 0-based rank of the lower middle among the
-        // alive rows.  d = rc + ones = rank - zeros decides the bit; rc becomes d for bit 0, stays for bit 1.
-        int rc = ((nvalid - 1) >> 1) - nvalid;
-        uint32_t lo = 0u, hi = 0u;
-        int diverged = 0;                                // all-ones once the two middles sit in different sets
+        // Two independent rank selects, lower middle (rank (n-1)/2) and upper middle (rank n/2; the same element when the
+        // count is odd).  State of a select: rc = rank - (number of alive rows), always negative; with `ones` alive rows
+        // having the bit set, d = rc + ones = rank - zeros decides the bit (0 iff d < 0), rc becomes d for bit 0 and stays
+        // for bit 1, i.e. rc - ones * m with m = d >> 31.  Counts, state and result bits are IMADs (FMA pipe): per word and
+        // pass the LOP3 pipe sees the 4 mask operations only, per pass the two sign shifts.  acc collects sum_b m_b 2^b
+        // with m_b = -1 where the bit is 0, so the key is 0xFFFFFFFF + acc.
+        int rc = ((nvalid - 1) >> 1) - nvalid, rc2 = (nvalid >> 1) - nvalid;
+        int lo_acc = 0, hi_acc = 0;
+        const int NEG1 = -(int)one, TWO = (int)one << 1;
         const uint32_t *pl = planes + 31 * kNanThreads;   // plane b of group 0; group k is k * 32 planes further
 #pragma unroll 4
         for (int b = 31; b >= 0; --b, pl -= kNanThreads) {
             uint32_t P[NW];
-            int d = rc;
-            uint32_t any0 = 0u;                          // rows of the upper middle's set whose bit is 0
+            int n1 = 0, n2 = 0;                          // minus the number of alive rows with the bit set
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
                 P[k] = k < nw ? pl[k * 32 * kNanThreads] : 0u;
-                d = popc_acc32(alive[k] & P[k], d, one);
-                any0 |= alive2[k] & ~P[k];
+                n1 = imad32(__popc(alive[k] & P[k]), NEG1, n1);
+                n2 = imad32(__popc(alive2[k] & P[k]), NEG1, n2);
             }
-            const int m0 = d >> 31;                      // all-ones: rank < zeros, the bit is 0
-            rc = isel32(d, rc, m0);
-            lo |= ~(uint32_t)m0 & (1u << b);
-            const int m0_shared = (d + 1) >> 31;         // shared state: the upper middle has rank + 1
-            const int m0_own = any0 != 0u ? -1 : 0;      // own state: it is the minimum of its set
-            const int m2 = isel32(m0_own, m0_shared, diverged);
-            diverged |= m2 ^ m0;
-            hi |= ~(uint32_t)m2 & (1u << b);
+            const int m0 = imad32(n1, NEG1, rc) >> 31;   // all-ones: the bit is 0
+            const int m2 = imad32(n2, NEG1, rc2) >> 31;
+            rc = imad32(n1, m0, rc);
+            rc2 = imad32(n2, m2, rc2);
+            lo_acc = imad32(lo_acc, TWO, m0);
+            hi_acc = imad32(hi_acc, TWO, m2);
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
                 alive[k] &= P[k] ^ (uint32_t)m0;
                 alive2[k] &= P[k] ^ (uint32_t)m2;
             }
         }
-        const float a = value_of(lo);
-        const float c = (nvalid & 1) ? a : value_of(hi);  // an odd count has one middle
+        const float a = value_of(0xFFFFFFFFu + (uint32_t)lo_acc);
+        const float c = value_of(0xFFFFFFFFu + (uint32_t)hi_acc);
         res = __fdiv_rn(__fadd_rn(a, c), 2.0f);
     }
     const int64_t o = (int64_t)slot[v] * N + n;
