@@ -47,6 +47,9 @@ constexpr int kMaxNH = 16;                // T <= 256: at most 16 half groups (o
 #ifndef BGD_LDSM_TWOSEL_MAX
 #define BGD_LDSM_TWOSEL_MAX 4             // even T: two independent selects up to this many plane words per column
 #endif
+#ifndef BGD_LDSM_TREE
+#define BGD_LDSM_TREE 0                   // 1: partial sums / partial ORs in two chains (A/B: profiles/r2_ab_tree.txt)
+#endif
 #ifndef BGD_LDSM_IMADSTATE_MAX
 #define BGD_LDSM_IMADSTATE_MAX 4          // select state updated by IMAD (not LOP3) up to this many plane words per column
 #endif
@@ -351,9 +354,21 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
                     m0 = d >> 31;                        // all-ones: the bit is 0
                     rc = imad(nones, m0, rc);
                 } else {
+#if BGD_LDSM_TREE
+                    // two partial sums: the IMAD chain of a pass is half as long (4 warps per scheduler do not hide it all)
+                    d = rc;
+                    int d1 = 0;
+#pragma unroll
+                    for (int k = 0; k < NWC; ++k) {
+                        if (k & 1) d1 = popc_acc(alive[k] & plane(k, b), d1, one);
+                        else d = popc_acc(alive[k] & plane(k, b), d, one);
+                    }
+                    d = imad(d1, ONE, d);
+#else
                     d = rc;
 #pragma unroll
                     for (int k = 0; k < NWC; ++k) d = popc_acc(alive[k] & plane(k, b), d, one);
+#endif
                     m0 = d >> 31;
                     rc = isel(d, rc, m0);
                 }
@@ -369,8 +384,18 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
                     for (int k = 0; k < NWC; ++k) alive2[k] &= plane(k, b) ^ (uint32_t)m2;
                 } else if constexpr (EVEN) {
                     uint32_t any0 = 0u;                  // rows of the upper middle's set whose bit is 0
+#if BGD_LDSM_TREE
+                    uint32_t any1 = 0u;
+#pragma unroll
+                    for (int k = 0; k < NWC; ++k) {
+                        if (k & 1) any1 |= alive2[k] & ~plane(k, b);
+                        else any0 |= alive2[k] & ~plane(k, b);
+                    }
+                    any0 |= any1;
+#else
 #pragma unroll
                     for (int k = 0; k < NWC; ++k) any0 |= alive2[k] & ~plane(k, b);
+#endif
                     // shared state: the upper middle has rank + 1, its bit is 0 iff d + 1 < 0; own state: iff any0
                     const int m0_shared = imad(ONE, ONE, d) >> 31;
                     const int m0_own = imad(__popc(any0), NEG1, 0) >> 31;
