@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     const int stages = prm.stages;
     const uint32_t stage_bytes = (uint32_t)prm.rows_cap * kTileW;
     uint64_t *bar = reinterpret_cast<uint64_t *>(buf + (size_t)stages * stage_bytes);   // bar[s]: buffer s is full
-    // desc[s] = {T, alive mask of the last word, columns of the tile inside the frame, -, output address of the tile}:
+    // desc[s] = {T | columns of the tile inside the frame << 16, alive mask of the last word, output address of the tile}:
     // written by the lane that requests tile s, read by every lane once the tile has landed -- the consumers keep no
     // (video, column tile) cursor of their own and touch no table in global memory
     uint4 *desc = reinterpret_cast<uint4 *>(bar + 8);
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
             const int64_t col0 = (int64_t)ct * kTileW;
             const int64_t left = prm.N - col0;
             const uint64_t dst = reinterpret_cast<uint64_t>(prm.out + prm.vid_out[vid] * prm.N + col0);
-            desc[2 * slot] = make_uint4((uint32_t)T, __ldg(prm.vid_mask + vid), (uint32_t)(left < kTileW ? left : kTileW), 0u);
-            desc[2 * slot + 1] = make_uint4((uint32_t)dst, (uint32_t)(dst >> 32), 0u, 0u);
+            desc[slot] = make_uint4((uint32_t)T | ((uint32_t)(left < kTileW ? left : kTileW) << 16), __ldg(prm.vid_mask + vid),
+                                    (uint32_t)dst, (uint32_t)(dst >> 32));
         }
         mbar_arrive_expect_tx(bar_s, (uint32_t)T * (uint32_t)kTileW);
         if constexpr (COLS == 2) {
@@ -260,12 +260,11 @@ __global__ void __launch_bounds__(threads_of<NH, STRIPS>(), min_blocks<NH, STRIP
     for (; tile < num_tiles; tile += (int)gridDim.x) {
         mbar_wait(bar + slot, (phases >> slot) & 1u);
         phases ^= 1u << slot;
-        const uint4 d0 = desc[2 * slot];
-        const uint2 d1 = *reinterpret_cast<const uint2 *>(desc + 2 * slot + 1);
-        const int T = (int)d0.x;
+        const uint4 d0 = desc[slot];
+        const int T = (int)(d0.x & 0xFFFFu);
         const uint32_t last_mask = d0.y;
-        const int cols_valid = (int)d0.z;
-        uint8_t *dst = reinterpret_cast<uint8_t *>(((uint64_t)d1.y << 32) | d1.x);
+        const int cols_valid = (int)(d0.x >> 16);
+        uint8_t *dst = reinterpret_cast<uint8_t *>(((uint64_t)d0.w << 32) | d0.z);
         const uint32_t ld_slot = ld_base + (uint32_t)slot * stage_bytes;
 
         // ---- shared memory -> registers (transposing loads), then 8x8 bit transposes -----------

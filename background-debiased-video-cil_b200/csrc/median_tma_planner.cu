@@ -250,11 +250,11 @@ int median_tma_varlen(const uint8_t *d_frames, const int64_t *h_offsets, int64_t
             const int blocks = tn.ldsm_blocks > 0 ? tn.ldsm_blocks
                                : (key.NW <= 6 ? 16 : (key.NW <= 12 ? 8 : (key.NW <= ldsm::kMaxNH ? 6 : (key.NW <= 24 ? 3 : 2)))) / lprm.strips;
             const size_t per_block = (size_t)dp.smem_per_sm / blocks - 1024;
-            int stages = tn.ldsm_stages > 0 ? tn.ldsm_stages : (int)((per_block - 1024 - 64 - 256) / tile_bytes);
+            int stages = tn.ldsm_stages > 0 ? tn.ldsm_stages : (int)((per_block - 1024 - 64 - 128) / tile_bytes);
             stages = std::max(1, std::min(stages, tn.ldsm_stages > 0 ? 8 : 4));
             lprm.stages = stages;
             lprm.max_blocks_per_sm = blocks;
-            const size_t smem = (size_t)stages * tile_bytes + 64 + 256 + 1024;       // tiles, 8 mbarriers, 8 tile descriptors, alignment slack
+            const size_t smem = (size_t)stages * tile_bytes + 64 + 128 + 1024;       // tiles, 8 mbarriers, 8 tile descriptors of 16 bytes, alignment slack
             rc = ldsm::launch(key.NW, key.even != 0, lprm, dp.sm_count, smem, stream);
             if (rc) break;
             pos += nv;
