@@ -224,6 +224,36 @@ def test_gather_of_extracted_backgrounds_equals_decoding_the_directory(tmp_path)
         assert names == ["r0_0", "r1_0", "r1_1", "r1_2"] and [int(b[0, 0]) for b in bgs] == [0, 10, 11, 12]
 
 
+def _gather_empty_worker(rank, world, port, bg_dir, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bgdebias_b200.pool import gather_extracted_backgrounds
+    paths, pool = gather_extracted_backgrounds(bg_dir, ".jpg", None, "cpu")
+    q.put((rank, paths, len(pool), [int(s["offset"]) for s in pool.slots], int(pool.slots["xtab"][0]) if len(pool) else None))
+    dist.destroy_process_group()
+
+
+def test_gather_with_an_empty_shard(tmp_path):
+    """More ranks than files (the ceil split leaves later ranks empty, extract_background.py:128-133): the empty rank sends
+    nothing and still ends up with the whole pool; bg_resize=None means no resize tables at all."""
+    import multiprocessing as mp
+    import cv2
+    cv2.imwrite(str(tmp_path / "only.jpg"), np.full((20, 24, 3), 77, np.uint8))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_empty_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, paths, n, offs, xtab in res:
+        assert paths == [str(tmp_path / "only.jpg")] and n == 1 and offs == [0] and xtab == -1
+
+
 def test_background_store_slots_without_gpu():
     """BackgroundStore on the CPU device: names are decoded once, pools are slot tables over shared pixels."""
     import numpy as np
