@@ -254,3 +254,33 @@ def test_dataset_ships_unresized_crops(env, tmp_path):
     out = ds.device_finish(ds.host_collate(same))
     exp = bo.mix_batch(np.stack([ro.resize_clip(clips[0], H, W)] * 2), resized_pool, [0, 0], [0, 0], [0, 0], [0, 0], crop=(H, W))
     np.testing.assert_array_equal(out["imgs"].cpu().numpy().view(np.uint32), exp.view(np.uint32))
+
+
+def test_unresized_crops_with_a_mixed_size_pool(env, tmp_path):
+    """The same pipeline (crops of mixed sizes, Resize on the device) over a pool of mixed image sizes: the foreground
+    Resize runs as its own launch, then the ragged-pool blend -- equal to Resize -> Normalize -> _mix_background with each
+    background resized and cropped at its own size (comix_loader.py:72-75,138-145)."""
+    from oracle import aa_resize_oracle as ao
+    ops, cabi, cl, pool_mod = env
+    rng = np.random.default_rng(19)
+    T, H, W, n = 2, 32, 32, 8
+    shapes = [(36, 36), (32, 32), (28, 32), (24, 28), (32, 36), (36, 32), (28, 28), (24, 24)]
+    clips = [rng.integers(0, 256, (T, h, w, 3), dtype=np.uint8) for h, w in shapes]
+    ra = np.zeros(n, bool)
+    names = [f"v{i:02d}" for i in range(4)]
+    for nm in names:
+        (tmp_path / (nm + ".jpg")).write_bytes(b"stub")
+    bg_sizes = [(36, 48), (36, 64), (50, 40), (80, 100)]
+    table = {str((tmp_path / (nm + ".jpg")).resolve()): rng.integers(0, 256, (3,) + bg_sizes[i], dtype=np.uint8) for i, nm in enumerate(names)}
+    infos = [dict(frame_dir=f"/x/{names[i % 4]}", total_frames=T, label=i, sample=i) for i in range(n)]
+    ds = cl.BackgroundMixDataset(infos, _CropPipeline(clips, ra), bg_dir=str(tmp_path), bg_resize=40, bg_crop_size=(H, W),
+                                 with_randAug=True, device_mix=True, bg_reader=_Reader(table))
+    torch.manual_seed(5)
+    samples = [ds.prepare_train_frames(i) for i in range(n)]
+    batch = ds.host_collate(samples)
+    assert batch["imgs"].dim() == 1 and batch["fg_geom"].shape == (n, 5)
+    out = ds.device_finish(batch)["imgs"].cpu().numpy()
+    assert ds.device_pool().tensor is None
+    exp = np.stack([bo.mix_clip(ro.resize_clip(clips[i], H, W), ao.aa_resize(table[ds.bg_files[s["bg_idx"]]], 40), s["bg_top"], s["bg_left"],
+                                (H, W), 0.5, True) for i, s in enumerate(samples)])
+    np.testing.assert_array_equal(out.view(np.uint32), exp.view(np.uint32))
